@@ -1,0 +1,89 @@
+"""Seeded synthetic inputs for the composed-retrieval scoring path.
+
+There is no dataset or checkpoint access (no network), so every parity test, golden
+fixture and benchmark feeds the path with features drawn from seeded torch CPU generators.
+The same functions are used by ``oracle/make_golden.py`` (which runs the unmodified
+reference on them) and by ``tests/`` / ``bench.py`` (which run the CUDA path), so both
+sides see bit-identical inputs.  Shapes follow SURVEY.md section 8(d).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+PATCHES = 13   # reference: run/test/test_fiq.py:130 (--patch-num)
+TOKENS = 77    # reference: run/test/test_fiq.py:98  (context_length=77)
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def combiner_state(seed: int, dim: int, scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """State dict of one ``CombinerSimple(dim, 4*dim, 8*dim)`` with the reference's key names
+    (models/fusion_model.py:73-84), values drawn like torch's default Linear init
+    (uniform in +-1/sqrt(fan_in)) from an explicit generator so the draw does not depend on
+    module construction order."""
+    g = _gen(seed)
+    proj, hid = 4 * dim, 8 * dim
+
+    def lin(out_f, in_f):
+        b = scale / np.sqrt(in_f)
+        w = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * b
+        bias = (torch.rand(out_f, generator=g) * 2 - 1) * b
+        return w, bias
+
+    sd: Dict[str, torch.Tensor] = {}
+    sd["dynamic_scalar.0.weight"], sd["dynamic_scalar.0.bias"] = lin(hid, 2 * proj)
+    sd["dynamic_scalar.3.weight"], sd["dynamic_scalar.3.bias"] = lin(1, hid)
+    sd["text_projection_layer.0.weight"], sd["text_projection_layer.0.bias"] = lin(proj, dim)
+    sd["image_projection_layer.0.weight"], sd["image_projection_layer.0.bias"] = lin(proj, dim)
+    # make the gate informative: default init gives |logit| << 1, i.e. s ~ 0.5 everywhere
+    sd["dynamic_scalar.3.weight"] = sd["dynamic_scalar.3.weight"] * 40.0
+    return sd
+
+
+def features(seed: int, rows: int, dim: int, unit: bool = False) -> torch.Tensor:
+    x = torch.randn(rows, dim, generator=_gen(seed))
+    if unit:
+        x = torch.nn.functional.normalize(x, dim=-1)
+    return x
+
+
+def patch_features(seed: int, rows: int, dim: int, patches: int = PATCHES) -> torch.Tensor:
+    return torch.randn(rows, patches, dim, generator=_gen(seed))
+
+
+def token_features(seed: int, rows: int, dim: int, tokens: int = TOKENS) -> torch.Tensor:
+    return torch.randn(rows, tokens, dim, generator=_gen(seed))
+
+
+def unique_names(n: int, fmt: str = "B{:07d}") -> List[str]:
+    return [fmt.format(i) for i in range(n)]
+
+
+def caption_names(seed: int, n: int, classes: int) -> List[str]:
+    """Fashion200k-style non-unique gallery 'names' (captions; dataloader/fashion200k_patch.py:287)."""
+    cls = torch.randint(0, classes, (n,), generator=_gen(seed)).tolist()
+    return [f"caption {c}" for c in cls]
+
+
+def planted_ranks(seed: int, q: int, max_rank: int = 100) -> torch.Tensor:
+    """Target rank per query with forced mass at the K boundaries."""
+    g = _gen(seed)
+    r = torch.randint(0, max_rank, (q,), generator=g)
+    edges = torch.tensor([0, 4, 5, 9, 10, 49, 50])
+    pick = torch.rand(q, generator=g) < 0.5
+    r[pick] = edges[torch.randint(0, len(edges), (int(pick.sum()),), generator=g)]
+    return r
+
+
+def tensor_digest(t: torch.Tensor) -> str:
+    """Stable fingerprint used to check that a regenerated tensor equals the one a golden was made from."""
+    a = t.detach().cpu().contiguous().numpy()
+    return hashlib.sha256(a.tobytes()).hexdigest()[:16]

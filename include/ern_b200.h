@@ -1,0 +1,164 @@
+/*
+ * ern_b200.h -- C ABI of libern_b200.so: the B200-native (sm_100a) composed-retrieval scoring path.
+ *
+ * The reference (ChenAnno/FashionERN_AAAI2024) is pure Python/PyTorch and has no FFI layer; its
+ * "operator API" for this path is (i) the module CombinerSimple (models/fusion_model.py:58-94) and
+ * (ii) the tails of compute_{fiq,shoes,200k,cirr}_val_metrics (run/test/test_fiq.py:44-64,
+ * test_shoes.py:44-61, test_200k.py:46-61, test_cirr.py:46-80, test_val.py:45-67 and the
+ * run/valid/validate_*.py twins).  Each entry point below names the reference lines it replaces.
+ * The Python mirror of those two surfaces lives in fashionern_aaai2024_b200/ and binds this
+ * header with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev / documented "device" is a CUDA device pointer
+ *     owned by the caller (e.g. torch.Tensor.data_ptr()); the library allocates nothing persistent.
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous.
+ *   - scratch is caller-provided: query the size with the matching *_workspace_bytes().
+ *   - every call returns 0 on success, <0 on error; ern_last_error() returns a thread-local message.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x calls fail with
+ *     ERN_ERR_DEVICE.
+ */
+#ifndef ERN_B200_H_
+#define ERN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ERN_OK 0
+#define ERN_ERR_ARG (-1)
+#define ERN_ERR_CUDA (-2)
+#define ERN_ERR_DEVICE (-3)
+#define ERN_ERR_WORKSPACE (-4)
+#define ERN_ERR_UNSUPPORTED (-5)
+
+/* arithmetic mode */
+#define ERN_MODE_BF16 0 /* bf16 operands, fp32 accumulate, tcgen05 tensor cores (the product path)   */
+#define ERN_MODE_FP32 1 /* fp32 FFMA "validation mode": 1e-5 parity with the reference's fp32 torch  */
+
+/* element type of a feature matrix handed to the library */
+#define ERN_DTYPE_F32 0
+#define ERN_DTYPE_BF16 1
+
+/* what a candidate is ranked by */
+#define ERN_RANK_SIMILARITY 0 /* s = <q, g>                                                       */
+#define ERN_RANK_REFERENCE 1  /* -(1 - s) rounded in fp32: the reference's `1 - pred @ index.T`    */
+                              /* (run/test/test_fiq.py:49) with its rounding-induced ties          */
+
+/* max k of the streaming top-k, and per-query capacity of the candidate list */
+#define ERN_MAX_K 128
+#define ERN_LIST_CAP 2048
+
+int ern_version(void);
+const char* ern_last_error(void);
+/* 0 iff `device` exists and is sm_100-class; the product refuses to run elsewhere. */
+int ern_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row L2-normalise (+ optional bf16 cast).
+ * Replaces F.normalize(index_features, dim=-1).float() (run/test/test_fiq.py:45 and twins),
+ * eps = 1e-12 as torch's default.  Either output may be NULL.  ld* are row strides in elements.
+ * ------------------------------------------------------------------------------------------- */
+int ern_l2norm_rows(const float* x_dev, int64_t rows, int dim, int64_t ldx, int normalize,
+                    float* out_f32_dev, int64_t ld_f32, void* out_bf16_dev, int64_t ld_bf16,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fusion head: CombinerSimple.forward(image_features, text_features) in eval mode
+ * (models/fusion_model.py:86-94; parameters :73-84).  Weights are torch's fp32 row-major
+ * [out,in] Linear matrices; `packed_bf16` is the buffer filled by ern_combiner_pack (needed for
+ * ERN_MODE_BF16 only).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ern_combiner_weights {
+  const float* w_text;  /* text_projection_layer.0.weight  [4D, D]  */
+  const float* b_text;  /* text_projection_layer.0.bias    [4D]     */
+  const float* w_image; /* image_projection_layer.0.weight [4D, D]  */
+  const float* b_image; /* image_projection_layer.0.bias   [4D]     */
+  const float* w_hid;   /* dynamic_scalar.0.weight         [8D, 8D] */
+  const float* b_hid;   /* dynamic_scalar.0.bias           [8D]     */
+  const float* w_gate;  /* dynamic_scalar.3.weight         [1, 8D]  */
+  const float* b_gate;  /* dynamic_scalar.3.bias           [1]      */
+  const void* packed_bf16;
+} ern_combiner_weights;
+
+size_t ern_combiner_packed_bytes(int dim);
+int ern_combiner_pack(const ern_combiner_weights* w, int dim, void* packed_dev, void* stream);
+size_t ern_combiner_workspace_bytes(int64_t rows, int dim, int mode);
+/* out_f32 [rows, D] unit-norm fused features; out_bf16 (nullable) the same rounded to bf16 with row
+ * stride ld_bf16 (ready to be a query/gallery operand of ern_sim_topk); gate (nullable) [rows] the
+ * dynamic scalar s. */
+int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const float* image_dev,
+                         const float* text_dev, int64_t rows, float* out_f32_dev,
+                         void* out_bf16_dev, int64_t ld_bf16, float* gate_dev, void* workspace_dev,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Similarity + streaming per-query top-k over one gallery shard.
+ * Replaces `distances = 1 - predicted_features @ index_features.T;
+ *           sorted_indices = torch.argsort(distances, dim=-1)` (run/test/test_fiq.py:49-50 and twins)
+ * for the first k columns; the [Q,N] matrix is never materialised.
+ *
+ *   queries   [nq, dim]   row stride ldq,  dtype q_dtype (F32 for MODE_FP32; BF16 for MODE_BF16)
+ *   gallery   [n_rows, dim] row stride ldg, same dtype; n_rows rows of this shard
+ *   id_offset global id of gallery row 0 (shard offset); ids returned are global
+ *   exclude_id_dev (nullable) [nq] global id removed from query q's ranking (CIRR reference image,
+ *             run/test/test_cirr.py:55-58); -1 = none
+ *   out_scores [nq,k] fp32 ranking value (similarity, or -(1-s) for ERN_RANK_REFERENCE), best first;
+ *   out_ids    [nq,k] int32 global ids, ties -> lower id first; missing entries: score -inf, id -1
+ *   out_keys   (nullable) [nq,k] uint64 sortable (value,id) keys, the wire format of the multi-GPU
+ *             candidate exchange (ern_topk_merge)
+ *   growth    gallery-range growth factor of the threshold schedule (>=2; 8 is the default);
+ *             growth == 1 selects the overflow-proof conservative schedule
+ *   status_dev int32[4]: [0] != 0 => a candidate list overflowed (pathologically ordered gallery):
+ *             results are NOT exact, call again with growth = 1.
+ * MODE_BF16 requires dim % 64 == 0, dim <= 640 and 16-byte aligned rows.
+ * ------------------------------------------------------------------------------------------- */
+size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode);
+int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
+                 int64_t n_rows, int64_t ldg, int dim, int dtype, int64_t id_offset,
+                 const int32_t* exclude_id_dev, int k, int mode, int rank_by, int growth,
+                 float* out_scores_dev, int32_t* out_ids_dev, uint64_t* out_keys_dev,
+                 int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * k-way merge of per-shard / per-rank candidate lists (after the NCCL all-gather of keys):
+ * list l of query q starts at keys_dev + l*list_stride + q*query_stride and holds k_in keys.
+ * n_lists * k_in <= ERN_LIST_CAP.
+ * ------------------------------------------------------------------------------------------- */
+int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, int64_t list_stride,
+                   int64_t query_stride, int k_out, float* out_scores_dev, int32_t* out_ids_dev,
+                   uint64_t* out_keys_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Recall@K from id membership on device.
+ * Replaces the numpy string gather/compare + slice + sum of run/test/test_fiq.py:51-60 (unique
+ * names) and run/test/test_200k.py:52-60 (any-hit on non-unique caption names):
+ *   rank[q] = first j < k with class_of[top_ids[q,j]] == target_class[q]  (k if none)
+ *   counts[i] = #{q : rank[q] < ks[i]}
+ * class_of_dev [n_gallery] int32 maps a global gallery id to its name class; ks is a HOST array.
+ * rank_dev (nullable) receives the per-query ranks.
+ * ------------------------------------------------------------------------------------------- */
+int ern_recall_at_k(const int32_t* top_ids_dev, int64_t nq, int k, const int32_t* class_of_dev,
+                    int64_t n_gallery, const int32_t* target_class_dev, const int32_t* ks, int nk,
+                    int32_t* counts_dev, int32_t* rank_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CIRR subset recall (run/test/test_cirr.py:64-66,76-78): rank of the target among the group
+ * members that are not the reference image, ordered by the same ranking value (ties -> lower id).
+ *   members_dev [nq, m] int32 gallery row ids (-1 = absent); rank_dev[q] = -1 if the target is not
+ *   among the surviving members (the reference asserts on that, test_cirr.py:69).
+ *   counts[i] = #{q : 0 <= rank[q] < ks[i]}
+ * ------------------------------------------------------------------------------------------- */
+int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
+                           int64_t n_rows, int64_t ldg, int dim, int dtype,
+                           const int32_t* members_dev, int m, const int32_t* reference_id_dev,
+                           const int32_t* target_id_dev, int rank_by, const int32_t* ks, int nk,
+                           int32_t* counts_dev, int32_t* rank_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ERN_B200_H_ */
