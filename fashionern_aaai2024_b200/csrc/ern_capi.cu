@@ -1,0 +1,335 @@
+// C ABI of libern_b200.so (declared in include/ern_b200.h): argument checking, launch plans, error strings.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ern_internal.cuh"
+#include "ern_select.cuh"
+
+namespace ern {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+  return ERN_ERR_CUDA;
+}
+
+struct DeviceInfo {
+  int device = -1;
+  int major = 0, minor = 0;
+  int sm_count = 0;
+};
+static int current_device(DeviceInfo* out) {
+  static thread_local DeviceInfo cache;
+  int dev = -1;
+  ERN_CUDA(cudaGetDevice(&dev));
+  if (cache.device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    ERN_CUDA(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev));
+    ERN_CUDA(cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    ERN_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    cache = d;
+  }
+  *out = cache;
+  if (cache.major != 10) {
+    set_error("device %d is sm_%d%d; libern_b200 only runs on sm_100-class (B200) GPUs and has no fallback", dev,
+              cache.major, cache.minor);
+    return ERN_ERR_DEVICE;
+  }
+  return ERN_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct SimWorkspace {
+  uint64_t* lists;
+  int32_t* counts;
+  float* thr;
+  size_t bytes;
+};
+static SimWorkspace carve_sim(void* base, int64_t nq) {
+  SimWorkspace w;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  w.lists = reinterpret_cast<uint64_t*>(p + off);
+  off += align256(static_cast<size_t>(nq) * ERN_LIST_CAP * 8);
+  w.counts = reinterpret_cast<int32_t*>(p + off);
+  off += align256(static_cast<size_t>(nq) * 4);
+  w.thr = reinterpret_cast<float*>(p + off);
+  off += align256(static_cast<size_t>(nq) * 4);
+  w.bytes = off;
+  return w;
+}
+
+// test hook: ERN_FORCE_SINGLE_CTA=1 makes the tensor-core path use the 1-CTA kernel even for large batches
+static int force_single() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ERN_FORCE_SINGLE_CTA");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
+}  // namespace ern
+
+using namespace ern;
+
+extern "C" {
+
+int ern_version(void) { return 100; }
+
+const char* ern_last_error(void) { return g_err; }
+
+int ern_device_check(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+  if (device < 0 || device >= n) {
+    set_error("device %d does not exist (%d visible)", device, n);
+    return ERN_ERR_DEVICE;
+  }
+  int major = 0;
+  ERN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) {
+    set_error("device %d is not sm_100-class (major %d)", device, major);
+    return ERN_ERR_DEVICE;
+  }
+  return ERN_OK;
+}
+
+int ern_l2norm_rows(const float* x_dev, int64_t rows, int dim, int64_t ldx, int normalize, float* out_f32_dev,
+                    int64_t ld_f32, void* out_bf16_dev, int64_t ld_bf16, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(x_dev && rows >= 0 && dim > 0 && ldx >= dim, "bad input matrix");
+  ERN_REQUIRE(out_f32_dev || out_bf16_dev, "no output requested");
+  return launch_l2norm_rows(x_dev, rows, dim, ldx, normalize, out_f32_dev, ld_f32, out_bf16_dev, ld_bf16,
+                            static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+size_t ern_combiner_packed_bytes(int dim) { return combiner::packed_bytes(dim); }
+
+int ern_combiner_pack(const ern_combiner_weights* w, int dim, void* packed_dev, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(w && packed_dev && dim > 0, "bad arguments");
+  ERN_REQUIRE(w->w_text && w->b_text && w->w_image && w->b_image && w->w_hid && w->b_hid && w->w_gate && w->b_gate,
+              "all eight parameter tensors are required");
+  return combiner::pack(w, dim, packed_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t ern_combiner_workspace_bytes(int64_t rows, int dim, int mode) {
+  if (rows < 0 || dim <= 0) return 0;
+  return mode == ERN_MODE_FP32 ? combiner::workspace_bytes_f32(rows, dim) : combiner::workspace_bytes_bf16(rows, dim);
+}
+
+int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const float* image_dev,
+                         const float* text_dev, int64_t rows, float* out_f32_dev, void* out_bf16_dev,
+                         int64_t ld_bf16, float* gate_dev, void* workspace_dev, size_t workspace_bytes,
+                         void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(w && image_dev && text_dev && rows >= 0 && dim > 0, "bad arguments");
+  ERN_REQUIRE(out_f32_dev || out_bf16_dev, "no output requested");
+  ERN_REQUIRE(!out_bf16_dev || ld_bf16 >= dim, "ld_bf16 < dim");
+  if (workspace_bytes < ern_combiner_workspace_bytes(rows, dim, mode) || (!workspace_dev && rows > 0)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, ern_combiner_workspace_bytes(rows, dim, mode));
+    return ERN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == ERN_MODE_FP32) {
+    ERN_REQUIRE(w->w_text && w->b_text && w->w_image && w->b_image && w->w_hid && w->b_hid && w->w_gate && w->b_gate,
+                "fp32 mode needs the eight fp32 parameter tensors");
+    return combiner::forward_f32(w, dim, image_dev, text_dev, rows, out_f32_dev, out_bf16_dev, ld_bf16, gate_dev,
+                                 workspace_dev, st);
+  }
+  if (mode == ERN_MODE_BF16) {
+    ERN_REQUIRE(w->packed_bf16, "bf16 mode needs packed weights (ern_combiner_pack)");
+    if (dim % 64 != 0) {
+      set_error("bf16 combiner needs dim %% 64 == 0 (got %d)", dim);
+      return ERN_ERR_UNSUPPORTED;
+    }
+    return combiner::forward_bf16(w, dim, image_dev, text_dev, rows, out_f32_dev, out_bf16_dev, ld_bf16, gate_dev,
+                                  workspace_dev, di.sm_count, st);
+  }
+  set_error("unknown mode %d", mode);
+  return ERN_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode) {
+  (void)dim;
+  (void)mode;
+  if (nq < 0) return 0;
+  return carve_sim(nullptr, nq).bytes + 256;
+}
+
+int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
+                 int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* exclude_id_dev, int k, int mode,
+                 int rank_by, int growth, float* out_scores_dev, int32_t* out_ids_dev, uint64_t* out_keys_dev,
+                 int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ERN_REQUIRE(nq >= 0 && n_rows >= 0 && dim > 0, "negative sizes");
+  ERN_REQUIRE(k >= 1 && k <= ERN_MAX_K, "k must be in [1,%d] (got %d)", ERN_MAX_K, k);
+  ERN_REQUIRE(rank_by == ERN_RANK_SIMILARITY || rank_by == ERN_RANK_REFERENCE, "bad rank_by %d", rank_by);
+  ERN_REQUIRE(growth >= 1 && growth <= 64, "growth must be in [1,64]");
+  ERN_REQUIRE(status_dev != nullptr, "status_dev is required");
+  ERN_REQUIRE(out_scores_dev || out_ids_dev || out_keys_dev, "no output requested");
+  ERN_REQUIRE(id_offset >= 0 && id_offset + n_rows <= 0x7FFFFFFFll, "global ids must fit int32");
+  ERN_REQUIRE((mode == ERN_MODE_FP32 && dtype == ERN_DTYPE_F32) || (mode == ERN_MODE_BF16 && dtype == ERN_DTYPE_BF16),
+              "mode/dtype mismatch: FP32 mode takes f32 features, BF16 mode takes bf16 features");
+  if (nq == 0) return ERN_OK;
+  ERN_REQUIRE(queries_dev && (gallery_dev || n_rows == 0) && ldq >= dim && ldg >= dim, "bad feature matrices");
+  if (workspace_bytes < ern_sim_topk_workspace_bytes(nq, dim, mode) || !workspace_dev) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, ern_sim_topk_workspace_bytes(nq, dim, mode));
+    return ERN_ERR_WORKSPACE;
+  }
+  SimWorkspace ws = carve_sim(workspace_dev, nq);
+
+  CUtensorMap tq, tg;
+  if (mode == ERN_MODE_BF16) {
+    if (dim % 64 != 0 || dim > 640) {
+      set_error("bf16 scoring needs dim %% 64 == 0 and dim <= 640 (got %d); zero-pad the features", dim);
+      return ERN_ERR_UNSUPPORTED;
+    }
+    ERN_REQUIRE((reinterpret_cast<uintptr_t>(queries_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(gallery_dev) & 15) == 0 &&
+                    (ldq * 2) % 16 == 0 && (ldg * 2) % 16 == 0,
+                "bf16 feature rows must be 16-byte aligned");
+    rc = simtc::make_tmap_bf16_rows(&tq, queries_dev, nq, dim, ldq);
+    if (rc) return rc;
+    if (n_rows > 0) {
+      rc = simtc::make_tmap_bf16_rows(&tg, gallery_dev, n_rows, dim, ldg);
+      if (rc) return rc;
+    }
+  }
+
+  rc = launch_init_state(ws.counts, ws.thr, nq, status_dev, st);
+  if (rc) return rc;
+
+  CandidateSink sink;
+  sink.lists = ws.lists;
+  sink.counts = ws.counts;
+  sink.thresholds = ws.thr;
+  sink.exclude = exclude_id_dev;
+  sink.status = status_dev;
+  sink.cap = ERN_LIST_CAP;
+  sink.id_offset = id_offset;
+  sink.nq = nq;
+
+  SelectParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.src = ws.lists;
+  sp.query_stride = ERN_LIST_CAP;
+  sp.n_lists = 1;
+  sp.cap = ERN_LIST_CAP;
+  sp.k = k;
+  sp.list_out = ws.lists;
+  sp.out_stride = ERN_LIST_CAP;
+  sp.counts_out = ws.counts;
+  sp.thresholds = ws.thr;
+  sp.status = status_dev;
+
+  int64_t begin = 0;
+  bool first = true;
+  do {
+    int64_t end;
+    if (first) {
+      end = n_rows < ERN_LIST_CAP ? n_rows : ERN_LIST_CAP;
+    } else if (growth == 1) {
+      end = begin + (ERN_LIST_CAP - k);  // at most cap - k appends on top of k kept entries: cannot overflow
+    } else {
+      end = begin * growth;
+    }
+    if (end > n_rows) end = n_rows;
+    sink.dense = first ? 1 : 0;
+    sink.row_begin = begin;
+    sink.row_end = end;
+    if (end > begin) {
+      if (mode == ERN_MODE_FP32)
+        rc = simf32::launch(static_cast<const float*>(queries_dev), ldq, static_cast<const float*>(gallery_dev), ldg,
+                            dim, sink, rank_by, st);
+      else
+        rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, st);
+      if (rc) return rc;
+    }
+    const bool last = end >= n_rows;
+    sp.counts_in = first ? nullptr : ws.counts;
+    sp.dense_count = static_cast<int>(end - begin);
+    sp.out_scores = last ? out_scores_dev : nullptr;
+    sp.out_ids = last ? out_ids_dev : nullptr;
+    sp.out_keys = last ? out_keys_dev : nullptr;
+    rc = launch_select(sp, nq, st);
+    if (rc) return rc;
+    begin = end;
+    first = false;
+  } while (begin < n_rows);
+  return ERN_OK;
+}
+
+int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, int64_t list_stride,
+                   int64_t query_stride, int k_out, float* out_scores_dev, int32_t* out_ids_dev, uint64_t* out_keys_dev,
+                   void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(keys_dev && nq >= 0 && n_lists >= 1 && k_in >= 1, "bad arguments");
+  ERN_REQUIRE(static_cast<int64_t>(n_lists) * k_in <= ERN_LIST_CAP, "n_lists * k_in must be <= %d", ERN_LIST_CAP);
+  ERN_REQUIRE(k_out >= 1 && k_out <= ERN_MAX_K, "k_out must be in [1,%d]", ERN_MAX_K);
+  SelectParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.src = keys_dev;
+  sp.list_stride = list_stride;
+  sp.query_stride = query_stride;
+  sp.n_lists = n_lists;
+  sp.k_in = k_in;
+  sp.dense_count = k_in;
+  sp.cap = ERN_LIST_CAP;
+  sp.k = k_out;
+  sp.out_scores = out_scores_dev;
+  sp.out_ids = out_ids_dev;
+  sp.out_keys = out_keys_dev;
+  return launch_select(sp, nq, static_cast<cudaStream_t>(stream));
+}
+
+int ern_recall_at_k(const int32_t* top_ids_dev, int64_t nq, int k, const int32_t* class_of_dev, int64_t n_gallery,
+                    const int32_t* target_class_dev, const int32_t* ks, int nk, int32_t* counts_dev, int32_t* rank_dev,
+                    void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(top_ids_dev && class_of_dev && target_class_dev && ks && counts_dev && k >= 1 && nq >= 0, "bad arguments");
+  return launch_recall(top_ids_dev, nq, k, class_of_dev, n_gallery, target_class_dev, ks, nk, counts_dev, rank_dev,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
+                           int64_t ldg, int dim, int dtype, const int32_t* members_dev, int m,
+                           const int32_t* reference_id_dev, const int32_t* target_id_dev, int rank_by,
+                           const int32_t* ks, int nk, int32_t* counts_dev, int32_t* rank_dev, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(queries_dev && gallery_dev && members_dev && reference_id_dev && target_id_dev && ks && counts_dev,
+              "bad arguments");
+  ERN_REQUIRE(dtype == ERN_DTYPE_F32 || dtype == ERN_DTYPE_BF16, "bad dtype");
+  return launch_cirr_subset(queries_dev, nq, ldq, gallery_dev, n_rows, ldg, dim, dtype, members_dev, m,
+                            reference_id_dev, target_id_dev, rank_by, ks, nk, counts_dev, rank_dev,
+                            static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Prototypes of the per-file kernel launchers (host functions) used by the C ABI glue.
+#pragma once
+#include <cuda.h>
+#include "ern_common.cuh"
+
+namespace ern {
+
+struct SelectParams;
+int launch_select(const SelectParams& p, int64_t nq, cudaStream_t st);
+int launch_init_state(int32_t* counts, float* thr, int64_t nq, int32_t* status, cudaStream_t st);
+int launch_recall(const int32_t* top_ids, int64_t nq, int k, const int32_t* class_of, int64_t n_gallery,
+                  const int32_t* target_class, const int32_t* ks, int nk, int32_t* counts, int32_t* rank_out,
+                  cudaStream_t st);
+int launch_cirr_subset(const void* queries, int64_t nq, int64_t ldq, const void* gallery, int64_t n_rows,
+                       int64_t ldg, int dim, int dtype, const int32_t* members, int m, const int32_t* ref_id,
+                       const int32_t* tgt_id, int rank_by, const int32_t* ks, int nk, int32_t* counts,
+                       int32_t* rank_out, cudaStream_t st);
+int launch_l2norm_rows(const float* x, int64_t rows, int dim, int64_t ldx, int normalize, float* of, int64_t ldf,
+                       void* ob, int64_t ldb, cudaStream_t st);
+
+namespace simf32 {
+int launch(const float* Q, int64_t ldq, const float* G, int64_t ldg, int dim, const CandidateSink& sink, int rank_by,
+           cudaStream_t st);
+}
+namespace simtc {
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int dim, int64_t ld_elems);
+int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
+           int force_single, int sm_count, cudaStream_t st);
+}
+namespace combiner {
+// views into the buffer filled by ern_combiner_pack: bf16 K-major weight matrices + fp32 vectors
+struct PackedView {
+  const __nv_bfloat16 *wt, *wi, *w1;
+  const float *bt, *bi, *b1, *w2, *b2;
+};
+PackedView view_packed(const void* packed, int dim);
+int launch_finalize(const float* image, const float* text, int64_t rows, int dim, const float* partial, int n_tiles,
+                    const float* b_gate, float* out, void* out_bf16, int64_t ldb, float* gate, cudaStream_t st);
+int launch_cast_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
+size_t packed_bytes(int dim);
+int pack(const ern_combiner_weights* w, int dim, void* packed, cudaStream_t st);
+size_t workspace_bytes_f32(int64_t rows, int dim);
+int forward_f32(const ern_combiner_weights* w, int dim, const float* image, const float* text, int64_t rows,
+                float* out, void* out_bf16, int64_t ldb, float* gate, void* workspace, cudaStream_t st);
+size_t workspace_bytes_bf16(int64_t rows, int dim);
+int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, const float* text, int64_t rows,
+                 float* out, void* out_bf16, int64_t ldb, float* gate, void* workspace, int sm_count,
+                 cudaStream_t st);
+}
+
+}  // namespace ern

@@ -1,0 +1,338 @@
+// bf16 similarity + streaming top-k candidate filter on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// Computes, for a range of gallery rows, S = Q . G^T (fp32 accumulate) tile by tile and hands every score
+// that reaches the query's current threshold to the candidate sink -- the [Q,N] score matrix of the
+// reference (`1 - predicted_features @ index_features.T`, run/test/test_fiq.py:49) never exists in HBM.
+//
+// Shape of the computation per CTA (or CTA pair, kPair):
+//   A = 128 queries x D bf16, RESIDENT in shared memory for a whole work item (160 KB at D = 640),
+//   B = gallery rows streamed by TMA in 128-row x 64-column (16 KB, 128B-swizzled) stages, 4-deep ring,
+//   D = 128 x TILE_G fp32 accumulator in TMEM, double buffered (2 x TILE_G columns),
+//   kPair: the two CTAs of a cluster issue ONE cta_group::2 UMMA of M = 256 (128 queries per CTA) by
+//          N = 256 (each CTA streams half of the gallery tile), halving shared-memory operand traffic.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer (leader CTA only
+// in a pair), warps 2..5 = epilogue; epilogue thread (quadrant, lane) owns one query row: it reads the
+// row's scores with tcgen05.ld (32 columns at a time), max-reduces them and only walks the 32 values
+// when the maximum reaches the row's threshold.
+#include "ern_common.cuh"
+#include "ern_ptx.cuh"
+
+namespace ern {
+namespace simtc {
+
+constexpr int kBlockQ = 128;
+constexpr int kBlockG = 128;
+constexpr int kBlockK = 64;
+constexpr int kStages = 4;
+constexpr int kMaxKBlocks = 10;
+constexpr int kTileBytes = kBlockQ * kBlockK * 2;  // 16 KB: one 128 x 64 bf16 swizzled tile
+constexpr int kThreads = 192;
+constexpr int kSmemBytes = 1024 + (kMaxKBlocks + kStages) * kTileBytes + 256;
+
+struct Params {
+  CandidateSink sink;
+  int num_kblocks;
+  int n_qtiles;         // query tiles of (kPair ? 256 : 128) rows
+  int tiles_total;      // gallery tiles of TILE_G rows in [row_begin, row_end)
+  int tiles_per_chunk;
+  int n_chunks;
+};
+
+struct Barriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t a_full;
+  uint64_t a_empty;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool kPair, int kRankBy>
+__global__ void __launch_bounds__(kThreads, 1)
+sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                   const Params p) {
+  constexpr int kCta = kPair ? 2 : 1;
+  constexpr int kTileG = kPair ? 256 : 128;   // gallery rows per accumulator tile
+  constexpr int kAccCols = kTileG;            // fp32 accumulator columns per stage
+  constexpr int kTmemCols = 2 * kAccCols;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + kMaxKBlocks * kTileBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_raw + (smem_b + kStages * kTileBytes - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const int n_units = kPair ? (gridDim.x >> 1) : gridDim.x;
+  const int n_items = p.n_qtiles * p.n_chunks;
+  int32_t* status = p.sink.status;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->empty[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&bars->a_full), 1);
+    ptx::mbar_init(ptx::smem_u32(&bars->a_empty), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[s]), 4 * kCta);  // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_g);
+  }
+  if (warp == 1) ptx::tmem_alloc<kCta>(ptx::smem_u32(&bars->tmem_base), kTmemCols);
+  ptx::tc_fence_before();
+  if (kPair) ptx::cluster_sync_all(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      const uint32_t a_full_dst = kPair ? ptx::mapa(ptx::smem_u32(&bars->a_full), 0) : ptx::smem_u32(&bars->a_full);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int item = unit; item < n_items; item += n_units, ++it) {
+        const int qt = item % p.n_qtiles;
+        const int chunk = item / p.n_qtiles;
+        const int q_row = qt * (kBlockQ * kCta) + rank * kBlockQ;
+        // A buffer is free once every MMA of the previous item has retired
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), (it & 1) ^ 1, status, 1);
+        if (leader) ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bars->a_full), p.num_kblocks * kTileBytes * kCta);
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          if (kPair) ptx::tma_load_2d_pair(smem_a + kb * kTileBytes, &tmap_q, kb * kBlockK, q_row, a_full_dst);
+          else       ptx::tma_load_2d(smem_a + kb * kTileBytes, &tmap_q, kb * kBlockK, q_row, a_full_dst);
+        }
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
+        for (int t = t0; t < t1; ++t) {
+          const int g_row = static_cast<int>(p.sink.row_begin) + t * kTileG + rank * kBlockG;
+          for (int kb = 0; kb < p.num_kblocks; ++kb) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, status, 2);
+            const uint32_t full = ptx::smem_u32(&bars->full[stage]);
+            if (leader) ptx::mbar_arrive_expect_tx(full, kTileBytes * kCta);
+            if (kPair) ptx::tma_load_2d_pair(smem_b + stage * kTileBytes, &tmap_g, kb * kBlockK, g_row, ptx::mapa(full, 0));
+            else       ptx::tma_load_2d(smem_b + stage * kTileBytes, &tmap_g, kb * kBlockK, g_row, full);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockQ * kCta, kTileG);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, it = 0;
+      for (int item = unit; item < n_items; item += n_units, ++it) {
+        const int chunk = item / p.n_qtiles;
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_full), it & 1, status, 3);
+        ptx::tc_fence_after();
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1, status, 4);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+          for (int kb = 0; kb < p.num_kblocks; ++kb) {
+            ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase, status, 5);
+            ptx::tc_fence_after();
+            const uint64_t adesc = ptx::smem_desc_sw128(smem_a + kb * kTileBytes);
+            const uint64_t bdesc = ptx::smem_desc_sw128(smem_b + stage * kTileBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advancing 16 bf16 (32 B) along K inside the 128 B swizzle atom = +2 in the address field
+              ptx::umma_bf16<kCta>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit<kCta>(ptx::smem_u32(&bars->empty[stage]));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          ptx::umma_commit<kCta>(ptx::smem_u32(&bars->tmem_full[acc]));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        ptx::umma_commit<kCta>(ptx::smem_u32(&bars->a_empty));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue ================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t empty_dst_base = ptx::smem_u32(&bars->tmem_empty[0]);
+    uint32_t acc = 0, acc_phase = 0;
+    const CandidateSink& sink = p.sink;
+    for (int item = unit; item < n_items; item += n_units) {
+      const int qt = item % p.n_qtiles;
+      const int chunk = item / p.n_qtiles;
+      const int64_t q = static_cast<int64_t>(qt) * (kBlockQ * kCta) + rank * kBlockQ + row_in_tile;
+      const bool q_ok = q < sink.nq;
+      const float thr = q_ok ? (sink.dense ? -INFINITY : sink.thresholds[q]) : INFINITY;
+      const int32_t excl = (q_ok && sink.exclude) ? sink.exclude[q] : -1;
+      const int t0 = chunk * p.tiles_per_chunk;
+      const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase, status, 6);
+        ptx::tc_fence_after();
+        const int64_t g_base = sink.row_begin + static_cast<int64_t>(t) * kTileG;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
+        uint32_t v[2][32];
+        ptx::tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+        for (int c = 0; c < kAccCols / 32; ++c) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < kAccCols / 32) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+          const uint32_t(&cur)[32] = v[c & 1];
+          float m = __uint_as_float(cur[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(cur[j]));
+          // dense launches store every row (NaN scores become empty slots), filter launches only survivors
+          if (sink.dense || rank_value<kRankBy>(m) >= thr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = rank_value<kRankBy>(__uint_as_float(cur[j]));
+              const int64_t row = g_base + c * 32 + j;
+              if ((sink.dense || r >= thr) && row < sink.row_end && q_ok) sink_put(sink, q, row, r, excl);
+            }
+          }
+        }
+        // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t dst = empty_dst_base + acc * 8;
+          if (kPair) ptx::mbar_arrive_cluster(ptx::mapa(dst, 0)); else ptx::mbar_arrive(dst);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+
+  // ================================ teardown ================================
+  ptx::tc_fence_before();
+  if (kPair) ptx::cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kCta>(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, dim] bf16 matrix -> boxes of 128 rows x 64 columns, 128-byte swizzle, zero OOB fill
+int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int dim, int64_t ld_elems) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return ERN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(kBlockQ)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld dim=%d ld=%lld base=%p)", (int)r,
+              (long long)rows, dim, (long long)ld_elems, base);
+    return ERN_ERR_CUDA;
+  }
+  return ERN_OK;
+}
+
+template <bool kPair, int kRankBy>
+static int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const Params& p, int grid, cudaStream_t st) {
+  auto kern = sim_topk_tc_kernel<kPair, kRankBy>;
+  static bool configured = false;
+  if (!configured) {
+    ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ERN_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tg, p));
+  return ERN_OK;
+}
+
+// Pick the chunking of [row_begin,row_end) that minimises the modelled makespan: items = qtiles x chunks are
+// dealt round-robin to the persistent units; every item pays one extra tile-time to (re)load its query tile.
+static void plan_chunks(int n_qtiles, int tiles_total, int units, int* n_chunks, int* tiles_per_chunk) {
+  long best_cost = -1;
+  int best_c = 1;
+  const int cmax = tiles_total < 8192 ? tiles_total : 8192;
+  for (int c = 1; c <= cmax; ++c) {
+    const long tpc = (tiles_total + c - 1) / c;
+    const long real_c = (tiles_total + tpc - 1) / tpc;
+    const long rounds = (static_cast<long>(n_qtiles) * real_c + units - 1) / units;
+    const long cost = rounds * (tpc + 1);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_c = static_cast<int>(real_c);
+    }
+  }
+  *tiles_per_chunk = (tiles_total + best_c - 1) / best_c;
+  *n_chunks = (tiles_total + *tiles_per_chunk - 1) / *tiles_per_chunk;
+}
+
+// One launch of the tensor-core scoring kernel over shard rows [sink.row_begin, sink.row_end).
+int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
+           int force_single, int sm_count, cudaStream_t st) {
+  const bool pair = !force_single && sink.nq > kBlockQ;
+  const int tile_g = pair ? 256 : 128;
+  Params p;
+  p.sink = sink;
+  p.num_kblocks = dim / kBlockK;
+  p.n_qtiles = cdiv(sink.nq, pair ? 2 * kBlockQ : kBlockQ);
+  p.tiles_total = cdiv(sink.row_end - sink.row_begin, tile_g);
+  if (p.tiles_total <= 0) return ERN_OK;
+  int units = pair ? sm_count / 2 : sm_count;
+  plan_chunks(p.n_qtiles, p.tiles_total, units, &p.n_chunks, &p.tiles_per_chunk);
+  const long items = static_cast<long>(p.n_qtiles) * p.n_chunks;
+  if (items < units) units = static_cast<int>(items);
+  const int grid = pair ? 2 * units : units;
+  if (pair) {
+    return rank_by == ERN_RANK_REFERENCE ? launch_one<true, ERN_RANK_REFERENCE>(tq, tg, p, grid, st)
+                                         : launch_one<true, ERN_RANK_SIMILARITY>(tq, tg, p, grid, st);
+  }
+  return rank_by == ERN_RANK_REFERENCE ? launch_one<false, ERN_RANK_REFERENCE>(tq, tg, p, grid, st)
+                                       : launch_one<false, ERN_RANK_SIMILARITY>(tq, tg, p, grid, st);
+}
+
+}  // namespace simtc
+}  // namespace ern

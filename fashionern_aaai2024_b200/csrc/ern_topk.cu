@@ -1,0 +1,270 @@
+// Candidate-list compaction / k-way merge, Recall@K, CIRR subset recall and row L2-normalisation kernels.
+// All of them are small HBM/latency-bound integer or reduction kernels next to the scoring GEMM.
+#include "ern_internal.cuh"
+#include "ern_select.cuh"
+
+namespace ern {
+
+// ------------------------------------------------------------------------------------------------------
+// Top-k selection of one query's candidate keys: bitonic sort (descending) of up to ERN_LIST_CAP keys in
+// shared memory.  Used (a) between scoring launches to tighten the per-query threshold, (b) to emit the
+// final sorted [k] (value, id) lists, (c) to merge lists gathered from other shards / ranks.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kSelectThreads = 256;
+
+
+__global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const SelectParams p) {
+  __shared__ uint64_t keys[ERN_LIST_CAP];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+
+  int n;
+  if (p.n_lists > 1 || p.counts_in == nullptr) {
+    n = (p.n_lists > 1) ? p.n_lists * p.k_in : p.dense_count;
+  } else {
+    const int c = p.counts_in[q];
+    if (c > p.cap && tid == 0 && p.status) atomicAdd(&p.status[0], 1);
+    n = c < p.cap ? c : p.cap;
+  }
+  int pow2 = 32;
+  while (pow2 < n) pow2 <<= 1;
+
+  if (p.n_lists > 1) {
+    for (int i = tid; i < pow2; i += kSelectThreads) {
+      uint64_t v = 0;
+      if (i < n) v = p.src[(i / p.k_in) * p.list_stride + q * p.query_stride + (i % p.k_in)];
+      keys[i] = v;
+    }
+  } else {
+    const uint64_t* src = p.src + q * p.query_stride;
+    for (int i = tid; i < pow2; i += kSelectThreads) keys[i] = i < n ? src[i] : 0ull;
+  }
+
+  // bitonic sort, descending
+  for (int size = 2; size <= pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < (pow2 >> 1); i += kSelectThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const uint64_t a = keys[lo], b = keys[hi];
+        const bool desc = (lo & size) == 0;
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const int k = p.k;
+  for (int j = tid; j < k; j += kSelectThreads) {
+    const uint64_t key = (j < pow2) ? keys[j] : 0ull;
+    if (p.list_out) p.list_out[q * p.out_stride + j] = key;
+    if (p.out_keys) p.out_keys[q * k + j] = key;
+    if (p.out_scores) p.out_scores[q * k + j] = key ? key_value(key) : -INFINITY;
+    if (p.out_ids) p.out_ids[q * k + j] = key ? key_id(key) : -1;
+  }
+  if (tid == 0) {
+    const uint64_t kth = (k - 1 < pow2) ? keys[k - 1] : 0ull;
+    int valid = n < k ? n : k;
+    if (p.counts_out) p.counts_out[q] = valid;
+    // a key of 0 inside the first k means fewer than k real candidates so far: no lower bound yet
+    if (p.thresholds) p.thresholds[q] = kth ? key_value(kth) : -INFINITY;
+  }
+}
+
+int launch_select(const SelectParams& p, int64_t nq, cudaStream_t st) {
+  if (nq <= 0) return ERN_OK;
+  select_topk_kernel<<<static_cast<unsigned>(nq), kSelectThreads, 0, st>>>(p);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+__global__ void init_state_kernel(int32_t* counts, float* thr, int64_t nq, int32_t* status) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < nq) {
+    counts[i] = 0;
+    thr[i] = -INFINITY;
+  }
+  if (i < 4 && status) status[i] = 0;
+}
+
+int launch_init_state(int32_t* counts, float* thr, int64_t nq, int32_t* status, cudaStream_t st) {
+  const int64_t n = nq < 4 ? 4 : nq;
+  init_state_kernel<<<cdiv(n, 256), 256, 0, st>>>(counts, thr, nq, status);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Recall@K: first position whose class equals the target's (run/test/test_fiq.py:51-60, test_200k.py:52-60)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxKs = 16;
+struct KList {
+  int32_t ks[kMaxKs];
+  int nk;
+};
+
+__global__ void recall_kernel(const int32_t* __restrict__ top_ids, int64_t nq, int k,
+                              const int32_t* __restrict__ class_of, int64_t n_gallery,
+                              const int32_t* __restrict__ target_class, KList kl, int32_t* counts,
+                              int32_t* rank_out) {
+  // one warp per query
+  const int64_t q = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const int32_t tc = target_class[q];
+  int best = k;
+  for (int j = lane; j < k; j += 32) {
+    const int32_t id = top_ids[q * k + j];
+    if (id >= 0 && id < n_gallery && class_of[id] == tc) {
+      best = j;
+      break;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) {
+    if (rank_out) rank_out[q] = best;
+    for (int i = 0; i < kl.nk; ++i)
+      if (best < kl.ks[i]) atomicAdd(&counts[i], 1);
+  }
+}
+
+__global__ void zero_i32_kernel(int32_t* p, int n) {
+  if (threadIdx.x < n) p[threadIdx.x] = 0;
+}
+
+int launch_recall(const int32_t* top_ids, int64_t nq, int k, const int32_t* class_of, int64_t n_gallery,
+                  const int32_t* target_class, const int32_t* ks, int nk, int32_t* counts, int32_t* rank_out,
+                  cudaStream_t st) {
+  ERN_REQUIRE(nk >= 1 && nk <= kMaxKs, "nk must be in [1,%d]", kMaxKs);
+  KList kl;
+  kl.nk = nk;
+  for (int i = 0; i < nk; ++i) kl.ks[i] = ks[i];
+  zero_i32_kernel<<<1, 32, 0, st>>>(counts, nk);
+  if (nq > 0) recall_kernel<<<cdiv(nq * 32, 256), 256, 0, st>>>(top_ids, nq, k, class_of, n_gallery, target_class, kl, counts, rank_out);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// CIRR subset recall (run/test/test_cirr.py:64-66,76-78): one warp per query scores the <= 8 group
+// members against the query and ranks the target among the members that are not the reference image.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, int64_t i);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, int64_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) {
+  return __bfloat162float(p[i]);
+}
+
+constexpr int kMaxMembers = 8;
+
+template <typename T>
+__global__ void cirr_subset_kernel(const T* __restrict__ queries, int64_t nq, int64_t ldq,
+                                   const T* __restrict__ gallery, int64_t n_rows, int64_t ldg, int dim,
+                                   const int32_t* __restrict__ members, int m,
+                                   const int32_t* __restrict__ ref_id, const int32_t* __restrict__ tgt_id,
+                                   int rank_by, KList kl, int32_t* counts, int32_t* rank_out) {
+  const int64_t q = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  float val[kMaxMembers];
+  int32_t ids[kMaxMembers];
+#pragma unroll
+  for (int j = 0; j < kMaxMembers; ++j) {
+    ids[j] = (j < m) ? members[q * m + j] : -1;
+    float acc = 0.f;
+    if (ids[j] >= 0 && ids[j] < n_rows) {
+      for (int d = lane; d < dim; d += 32)
+        acc = fmaf(load_as_float(queries, q * ldq + d), load_as_float(gallery, ids[j] * ldg + d), acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    val[j] = (rank_by == ERN_RANK_REFERENCE) ? -(1.0f - acc) : acc + 0.0f;
+  }
+  if (lane == 0) {
+    const int32_t r = ref_id[q], t = tgt_id[q];
+    int tpos = -1;
+    for (int j = 0; j < m; ++j)
+      if (ids[j] == t && ids[j] != r && ids[j] >= 0) tpos = j;
+    int rank = -1;
+    if (tpos >= 0) {
+      rank = 0;
+      for (int j = 0; j < m; ++j) {
+        if (j == tpos || ids[j] < 0 || ids[j] == r || ids[j] == t) continue;
+        bool dup = false;  // a member listed twice counts once
+        for (int i = 0; i < j; ++i) dup |= (ids[i] == ids[j]);
+        if (dup) continue;
+        if (val[j] > val[tpos] || (val[j] == val[tpos] && ids[j] < t)) ++rank;
+      }
+    }
+    if (rank_out) rank_out[q] = rank;
+    if (rank >= 0)
+      for (int i = 0; i < kl.nk; ++i)
+        if (rank < kl.ks[i]) atomicAdd(&counts[i], 1);
+  }
+}
+
+int launch_cirr_subset(const void* queries, int64_t nq, int64_t ldq, const void* gallery, int64_t n_rows,
+                       int64_t ldg, int dim, int dtype, const int32_t* members, int m, const int32_t* ref_id,
+                       const int32_t* tgt_id, int rank_by, const int32_t* ks, int nk, int32_t* counts,
+                       int32_t* rank_out, cudaStream_t st) {
+  ERN_REQUIRE(nk >= 1 && nk <= kMaxKs, "nk must be in [1,%d]", kMaxKs);
+  ERN_REQUIRE(m >= 1 && m <= kMaxMembers, "group size m must be in [1,%d]", kMaxMembers);
+  KList kl;
+  kl.nk = nk;
+  for (int i = 0; i < nk; ++i) kl.ks[i] = ks[i];
+  zero_i32_kernel<<<1, 32, 0, st>>>(counts, nk);
+  if (nq > 0) {
+    const int grid = cdiv(nq * 32, 256);
+    if (dtype == ERN_DTYPE_F32)
+      cirr_subset_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(queries), nq, ldq,
+                                                      static_cast<const float*>(gallery), n_rows, ldg, dim, members,
+                                                      m, ref_id, tgt_id, rank_by, kl, counts, rank_out);
+    else
+      cirr_subset_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(queries), nq, ldq, static_cast<const __nv_bfloat16*>(gallery), n_rows,
+          ldg, dim, members, m, ref_id, tgt_id, rank_by, kl, counts, rank_out);
+  }
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Row L2-normalise (F.normalize eps 1e-12) + optional bf16 cast; one warp per row, HBM-bound.
+// ------------------------------------------------------------------------------------------------------
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, int64_t rows, int dim, int64_t ldx, int normalize,
+                                   float* __restrict__ of, int64_t ldf, __nv_bfloat16* __restrict__ ob,
+                                   int64_t ldb) {
+  const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + r * ldx;
+  float denom = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int d = lane; d < dim; d += 32) ss = fmaf(xr[d], xr[d], ss);
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    denom = fmaxf(sqrtf(ss), 1e-12f);  // x / max(||x||, eps), torch's F.normalize
+  }
+  for (int d = lane; d < dim; d += 32) {
+    const float v = normalize ? xr[d] / denom : xr[d];
+    if (of) of[r * ldf + d] = v;
+    if (ob) ob[r * ldb + d] = __float2bfloat16_rn(v);
+  }
+}
+
+int launch_l2norm_rows(const float* x, int64_t rows, int dim, int64_t ldx, int normalize, float* of, int64_t ldf,
+                       void* ob, int64_t ldb, cudaStream_t st) {
+  if (rows <= 0) return ERN_OK;
+  l2norm_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(x, rows, dim, ldx, normalize, of, ldf,
+                                                           static_cast<__nv_bfloat16*>(ob), ldb);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+}  // namespace ern

@@ -1,0 +1,192 @@
+"""Tensor-level wrappers over the C ABI: torch owns memory and streams, libern_b200 does the work.
+
+Nothing here computes on the host or with torch ops -- torch is used for allocation, stream handles and
+(in callers) ``torch.distributed``.  All functions require CUDA tensors on an sm_100-class device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import (DTYPE_BF16, DTYPE_F32, LIST_CAP, MAX_K, MODE_BF16, MODE_FP32, RANK_REFERENCE,
+                   RANK_SIMILARITY, ErnError)
+
+__all__ = ["l2norm_rows", "sim_topk", "topk_merge", "recall_at_k", "cirr_subset_recall", "launch_counter"]
+
+
+class _LaunchCounter:
+    """Counts kernel launches issued through this module (bench.py reports it as ``gpu_launches``).
+    The numbers mirror what the C ABI launches per call ('launch accounting')."""
+
+    def __init__(self):
+        self.n = 0
+
+    def add(self, n: int):
+        self.n += int(n)
+
+
+launch_counter = _LaunchCounter()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _rowmajor(t: torch.Tensor, what: str) -> torch.Tensor:
+    L.require_cuda(t, what)
+    if t.dim() != 2:
+        raise ErnError(f"{what} must be 2-D, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def l2norm_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, want_bf16: bool = False
+                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """``F.normalize(x, dim=-1).float()`` (run/test/test_fiq.py:45) and/or its bf16 rounding, on device."""
+    x = _rowmajor(x, "x")
+    if x.dtype != torch.float32:
+        raise ErnError(f"l2norm_rows takes float32 features, got {x.dtype}")
+    rows, dim = x.shape
+    of = torch.empty((rows, dim), dtype=torch.float32, device=x.device) if want_f32 else None
+    ob = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    with torch.cuda.device(x.device):
+        L.check(L.lib().ern_l2norm_rows(x.data_ptr(), rows, dim, x.stride(0), int(normalize), L.ptr(of), dim,
+                                        L.ptr(ob), dim, L.stream_ptr(x.device)))
+    launch_counter.add(1 if rows else 0)
+    return of, ob
+
+
+def _phase_count(n_rows: int, k: int, growth: int) -> int:
+    if n_rows <= LIST_CAP:
+        return 1
+    n, begin = 1, LIST_CAP
+    while begin < n_rows:
+        begin = begin + (LIST_CAP - k) if growth == 1 else begin * growth
+        n += 1
+    return n
+
+
+def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int = MODE_BF16,
+             rank_by: int = RANK_SIMILARITY, exclude_ids: Optional[torch.Tensor] = None, id_offset: int = 0,
+             growth: int = 8, want_keys: bool = False, check_overflow: bool = True):
+    """Top-k gallery rows per query by cosine similarity; replaces ``1 - pred @ index.T`` + ``torch.argsort``
+    (run/test/test_fiq.py:49-50) without materialising the [Q,N] matrix.
+
+    Returns ``(values fp32 [Q,k], ids int32 [Q,k], keys uint64-as-int64 [Q,k] | None, status int32[4])``.
+    ``check_overflow=True`` reads ``status`` back (one host sync) and transparently re-runs with the
+    overflow-proof schedule if a candidate list overflowed; with ``False`` the caller must inspect it.
+    """
+    q = _rowmajor(queries, "queries")
+    g = _rowmajor(gallery, "gallery")
+    want = torch.float32 if mode == MODE_FP32 else torch.bfloat16
+    if q.dtype != want or g.dtype != want:
+        raise ErnError(f"mode {mode} takes {want} features, got queries {q.dtype} / gallery {g.dtype}")
+    if q.shape[1] != g.shape[1]:
+        raise ErnError(f"feature dims differ: {q.shape[1]} vs {g.shape[1]}")
+    if q.device != g.device:
+        raise ErnError("queries and gallery must live on the same device")
+    nq, dim = q.shape
+    n_rows = g.shape[0]
+    dev = q.device
+    vals = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    keys = torch.empty((nq, k), dtype=torch.int64, device=dev) if want_keys else None
+    status = torch.empty(4, dtype=torch.int32, device=dev)
+    if exclude_ids is not None:
+        L.require_cuda(exclude_ids, "exclude_ids")
+        exclude_ids = exclude_ids.to(torch.int32).contiguous()
+    lib = L.lib()
+    dtype = DTYPE_F32 if mode == MODE_FP32 else DTYPE_BF16
+    with torch.cuda.device(dev):
+        wsb = lib.ern_sim_topk_workspace_bytes(nq, dim, mode)
+        ws = _workspace(wsb, dev)
+
+        def run(gr):
+            L.check(lib.ern_sim_topk(q.data_ptr(), nq, q.stride(0), g.data_ptr(), n_rows, g.stride(0), dim, dtype,
+                                     int(id_offset), L.ptr(exclude_ids), int(k), mode, rank_by, gr,
+                                     vals.data_ptr(), ids.data_ptr(), L.ptr(keys), status.data_ptr(),
+                                     ws.data_ptr(), wsb, L.stream_ptr(dev)))
+            launch_counter.add(1 + 2 * _phase_count(n_rows, k, gr) if nq else 0)
+
+        run(growth)
+        if check_overflow and nq and int(status[0].item()) != 0:
+            run(1)
+            if int(status[0].item()) != 0:
+                raise ErnError("candidate list overflow even with the conservative schedule (internal error)")
+    return vals, ids, keys, status
+
+
+def topk_merge(keys: torch.Tensor, k_out: int):
+    """Merge per-shard sorted candidate lists ``keys`` [S, Q, k_in] (int64 view of the uint64 wire keys)
+    into the global top-``k_out`` per query -- the device-side k-way merge after the NCCL all-gather."""
+    L.require_cuda(keys, "keys")
+    if keys.dim() != 3 or keys.dtype != torch.int64:
+        raise ErnError("keys must be int64 [S, Q, k_in]")
+    keys = keys.contiguous()
+    s, nq, k_in = keys.shape
+    dev = keys.device
+    vals = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+    ids = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+    out_keys = torch.empty((nq, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ern_topk_merge(keys.data_ptr(), nq, s, k_in, nq * k_in, k_in, k_out, vals.data_ptr(),
+                                       ids.data_ptr(), out_keys.data_ptr(), L.stream_ptr(dev)))
+    launch_counter.add(1 if nq else 0)
+    return vals, ids, out_keys
+
+
+def _ks(ks: Sequence[int]):
+    arr = (C.c_int32 * len(ks))(*[int(x) for x in ks])
+    return arr, len(ks)
+
+
+def recall_at_k(top_ids: torch.Tensor, class_of: torch.Tensor, target_class: torch.Tensor, ks: Sequence[int]):
+    """Hit counts for Recall@K from id membership (run/test/test_fiq.py:51-60; any-hit for non-unique names,
+    run/test/test_200k.py:52-60).  Returns ``(counts int32[len(ks)], first_hit_rank int32[Q])`` on device."""
+    for t, n in ((top_ids, "top_ids"), (class_of, "class_of"), (target_class, "target_class")):
+        L.require_cuda(t, n)
+        if t.dtype != torch.int32:
+            raise ErnError(f"{n} must be int32")
+    top_ids, class_of, target_class = top_ids.contiguous(), class_of.contiguous(), target_class.contiguous()
+    nq, k = top_ids.shape
+    dev = top_ids.device
+    counts = torch.empty(len(ks), dtype=torch.int32, device=dev)
+    ranks = torch.empty(nq, dtype=torch.int32, device=dev)
+    arr, nk = _ks(ks)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ern_recall_at_k(top_ids.data_ptr(), nq, k, class_of.data_ptr(), class_of.numel(),
+                                        target_class.data_ptr(), arr, nk, counts.data_ptr(), ranks.data_ptr(),
+                                        L.stream_ptr(dev)))
+    launch_counter.add(2 if nq else 1)
+    return counts, ranks
+
+
+def cirr_subset_recall(queries: torch.Tensor, gallery: torch.Tensor, members: torch.Tensor,
+                       reference_ids: torch.Tensor, target_ids: torch.Tensor, ks: Sequence[int] = (1, 2, 3),
+                       rank_by: int = RANK_REFERENCE):
+    """CIRR subset recall (run/test/test_cirr.py:64-66,76-78).  ``members`` int32 [Q, m<=8] gallery rows.
+    Returns ``(counts int32[len(ks)], rank int32[Q])``; rank -1 where the target is not a surviving member."""
+    q = _rowmajor(queries, "queries")
+    g = _rowmajor(gallery, "gallery")
+    if q.dtype != g.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+        raise ErnError("queries/gallery must both be float32 or both bfloat16")
+    dtype = DTYPE_F32 if q.dtype == torch.float32 else DTYPE_BF16
+    members = members.to(torch.int32).contiguous()
+    reference_ids = reference_ids.to(torch.int32).contiguous()
+    target_ids = target_ids.to(torch.int32).contiguous()
+    nq, m = members.shape
+    dev = q.device
+    counts = torch.empty(len(ks), dtype=torch.int32, device=dev)
+    ranks = torch.empty(nq, dtype=torch.int32, device=dev)
+    arr, nk = _ks(ks)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ern_cirr_subset_recall(q.data_ptr(), nq, q.stride(0), g.data_ptr(), g.shape[0], g.stride(0),
+                                               q.shape[1], dtype, members.data_ptr(), m, reference_ids.data_ptr(),
+                                               target_ids.data_ptr(), rank_by, arr, nk, counts.data_ptr(),
+                                               ranks.data_ptr(), L.stream_ptr(dev)))
+    launch_counter.add(2 if nq else 1)
+    return counts, ranks

@@ -28,6 +28,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define ERN_API __attribute__((visibility("default")))
+#else
+#define ERN_API
+#endif
+
 #define ERN_OK 0
 #define ERN_ERR_ARG (-1)
 #define ERN_ERR_CUDA (-2)
@@ -52,17 +58,17 @@ extern "C" {
 #define ERN_MAX_K 128
 #define ERN_LIST_CAP 2048
 
-int ern_version(void);
-const char* ern_last_error(void);
+ERN_API int ern_version(void);
+ERN_API const char* ern_last_error(void);
 /* 0 iff `device` exists and is sm_100-class; the product refuses to run elsewhere. */
-int ern_device_check(int device);
+ERN_API int ern_device_check(int device);
 
 /* ---------------------------------------------------------------------------------------------
  * Row L2-normalise (+ optional bf16 cast).
  * Replaces F.normalize(index_features, dim=-1).float() (run/test/test_fiq.py:45 and twins),
  * eps = 1e-12 as torch's default.  Either output may be NULL.  ld* are row strides in elements.
  * ------------------------------------------------------------------------------------------- */
-int ern_l2norm_rows(const float* x_dev, int64_t rows, int dim, int64_t ldx, int normalize,
+ERN_API int ern_l2norm_rows(const float* x_dev, int64_t rows, int dim, int64_t ldx, int normalize,
                     float* out_f32_dev, int64_t ld_f32, void* out_bf16_dev, int64_t ld_bf16,
                     void* stream);
 
@@ -84,13 +90,13 @@ typedef struct ern_combiner_weights {
   const void* packed_bf16;
 } ern_combiner_weights;
 
-size_t ern_combiner_packed_bytes(int dim);
-int ern_combiner_pack(const ern_combiner_weights* w, int dim, void* packed_dev, void* stream);
-size_t ern_combiner_workspace_bytes(int64_t rows, int dim, int mode);
+ERN_API size_t ern_combiner_packed_bytes(int dim);
+ERN_API int ern_combiner_pack(const ern_combiner_weights* w, int dim, void* packed_dev, void* stream);
+ERN_API size_t ern_combiner_workspace_bytes(int64_t rows, int dim, int mode);
 /* out_f32 [rows, D] unit-norm fused features; out_bf16 (nullable) the same rounded to bf16 with row
  * stride ld_bf16 (ready to be a query/gallery operand of ern_sim_topk); gate (nullable) [rows] the
  * dynamic scalar s. */
-int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const float* image_dev,
+ERN_API int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const float* image_dev,
                          const float* text_dev, int64_t rows, float* out_f32_dev,
                          void* out_bf16_dev, int64_t ld_bf16, float* gate_dev, void* workspace_dev,
                          size_t workspace_bytes, void* stream);
@@ -116,8 +122,8 @@ int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const
  *             results are NOT exact, call again with growth = 1.
  * MODE_BF16 requires dim % 64 == 0, dim <= 640 and 16-byte aligned rows.
  * ------------------------------------------------------------------------------------------- */
-size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode);
-int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
+ERN_API size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode);
+ERN_API int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
                  int64_t n_rows, int64_t ldg, int dim, int dtype, int64_t id_offset,
                  const int32_t* exclude_id_dev, int k, int mode, int rank_by, int growth,
                  float* out_scores_dev, int32_t* out_ids_dev, uint64_t* out_keys_dev,
@@ -128,7 +134,7 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
  * list l of query q starts at keys_dev + l*list_stride + q*query_stride and holds k_in keys.
  * n_lists * k_in <= ERN_LIST_CAP.
  * ------------------------------------------------------------------------------------------- */
-int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, int64_t list_stride,
+ERN_API int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, int64_t list_stride,
                    int64_t query_stride, int k_out, float* out_scores_dev, int32_t* out_ids_dev,
                    uint64_t* out_keys_dev, void* stream);
 
@@ -141,7 +147,7 @@ int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, 
  * class_of_dev [n_gallery] int32 maps a global gallery id to its name class; ks is a HOST array.
  * rank_dev (nullable) receives the per-query ranks.
  * ------------------------------------------------------------------------------------------- */
-int ern_recall_at_k(const int32_t* top_ids_dev, int64_t nq, int k, const int32_t* class_of_dev,
+ERN_API int ern_recall_at_k(const int32_t* top_ids_dev, int64_t nq, int k, const int32_t* class_of_dev,
                     int64_t n_gallery, const int32_t* target_class_dev, const int32_t* ks, int nk,
                     int32_t* counts_dev, int32_t* rank_dev, void* stream);
 
@@ -152,7 +158,7 @@ int ern_recall_at_k(const int32_t* top_ids_dev, int64_t nq, int k, const int32_t
  *   among the surviving members (the reference asserts on that, test_cirr.py:69).
  *   counts[i] = #{q : 0 <= rank[q] < ks[i]}
  * ------------------------------------------------------------------------------------------- */
-int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
+ERN_API int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
                            int64_t n_rows, int64_t ldg, int dim, int dtype,
                            const int32_t* members_dev, int m, const int32_t* reference_id_dev,
                            const int32_t* target_id_dev, int rank_by, const int32_t* ks, int nk,

@@ -1,0 +1,76 @@
+"""CPU: the C-ABI library loads, exports exactly what include/ern_b200.h declares, and the product
+fails loudly (no CPU fallback) when there is no sm_100 device or a CPU tensor is passed."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from fashionern_aaai2024_b200 import _lib, ops
+from fashionern_aaai2024_b200.combiner import CombinerSimple
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    with open(os.path.join(ROOT, "include", "ern_b200.h")) as f:
+        src = f.read()
+    return re.findall(r"ERN_API\s+[\w\s\*]+?\b(ern_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    declared = header_symbols()
+    assert sorted(declared) == sorted(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_version_and_constants():
+    lib = _lib.lib()
+    assert lib.ern_version() >= 100
+    with open(os.path.join(ROOT, "include", "ern_b200.h")) as f:
+        src = f.read()
+    assert int(re.search(r"#define ERN_MAX_K (\d+)", src).group(1)) == _lib.MAX_K
+    assert int(re.search(r"#define ERN_LIST_CAP (\d+)", src).group(1)) == _lib.LIST_CAP
+    assert lib.ern_sim_topk_workspace_bytes(4096, 640, 0) >= 4096 * _lib.LIST_CAP * 8
+    assert lib.ern_combiner_packed_bytes(640) >= (8 * 640 * 640 + 64 * 640 * 640) * 2
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly():
+    rc = _lib.lib().ern_device_check(0)
+    assert rc != 0 and len(_lib.lib().ern_last_error()) > 0
+    with pytest.raises(_lib.ErnError):
+        _lib.check(rc)
+
+
+def test_cpu_tensors_are_refused():
+    x = torch.randn(4, 64)
+    with pytest.raises(_lib.ErnError):
+        ops.l2norm_rows(x)
+    with pytest.raises(_lib.ErnError):
+        ops.sim_topk(x, x, 2, mode=_lib.MODE_FP32)
+    m = CombinerSimple(64, 256, 512).eval()
+    with pytest.raises(_lib.ErnError):
+        m(x, x)
+
+
+def test_training_mode_is_refused():
+    m = CombinerSimple(64, 256, 512)
+    m.train()
+    with pytest.raises(_lib.ErnError):
+        m(torch.randn(2, 64), torch.randn(2, 64))
+
+
+def test_state_dict_keys_match_reference():
+    # models/fusion_model.py:73-84 -> the key names ERN.load_state_dict expects (run/test/test_fiq.py:149)
+    keys = set(CombinerSimple(64, 256, 512).state_dict().keys())
+    assert keys == {
+        "dynamic_scalar.0.weight", "dynamic_scalar.0.bias", "dynamic_scalar.3.weight", "dynamic_scalar.3.bias",
+        "text_projection_layer.0.weight", "text_projection_layer.0.bias",
+        "image_projection_layer.0.weight", "image_projection_layer.0.bias"}
+    sd = CombinerSimple(64, 256, 512).state_dict()
+    assert sd["dynamic_scalar.0.weight"].shape == (512, 512) and sd["dynamic_scalar.3.weight"].shape == (1, 512)
+    assert sd["text_projection_layer.0.weight"].shape == (256, 64)

@@ -1,0 +1,164 @@
+"""GPU: similarity + top-k (ern_sim_topk), merge, recall kernels against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ern_oracle as orc
+from fashionern_aaai2024_b200 import ops, synthetic as syn
+from fashionern_aaai2024_b200._lib import (MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARITY, ErnError)
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances: the CUDA and oracle scores are fp32 sums of the same products in a
+# different order, so they agree to a few ulp of the largest partial sums; ids must be identical except
+# where the ORACLE's own scores are closer than this.
+TOL_FP32 = 2e-6
+TOL_BF16_SAME_INPUTS = 2e-6   # oracle fed the same bf16-rounded operands: only accumulation order differs
+
+
+def unit(seed, rows, dim):
+    return syn.features(seed, rows, dim, unit=True)
+
+
+def run_case(dev, q, n, dim, k, mode, rank_by=RANK_REFERENCE, exclude=None, growth=8, seed=0):
+    pred, gal = unit(seed + 1, q, dim), unit(seed + 2, n, dim)
+    if mode == MODE_BF16:
+        pred_o, gal_o = pred.bfloat16().float(), gal.bfloat16().float()
+        qd, gd = pred.bfloat16().to(dev), gal.bfloat16().to(dev)
+        tol = TOL_BF16_SAME_INPUTS
+    else:
+        pred_o, gal_o = pred, gal
+        qd, gd = pred.to(dev), gal.to(dev)
+        tol = TOL_FP32
+    ex = None if exclude is None else exclude.to(dev)
+    vals, ids, keys, status = ops.sim_topk(qd, gd, k, mode=mode, rank_by=rank_by, exclude_ids=ex, growth=growth,
+                                           want_keys=True)
+    torch.cuda.synchronize()
+    ids_c, vals_c = ids.cpu().numpy(), vals.cpu().numpy()
+    sims = vals_c if rank_by == RANK_SIMILARITY else vals_c + 1.0   # -(1-s) -> s (approximately)
+    finite = np.where(np.isfinite(sims), sims, 0.0)
+    stats = orc.compare_topk(ids_c, finite, pred_o, gal_o, k, tol=tol + (0 if rank_by == RANK_SIMILARITY else 1.2e-7),
+                             exclude_index=exclude)
+    # rows are sorted best-first, ties by lower id
+    v = vals_c
+    assert np.all((v[:, :-1] >= v[:, 1:]) | ~np.isfinite(v[:, 1:]))
+    tie = (v[:, :-1] == v[:, 1:]) & np.isfinite(v[:, 1:])
+    assert np.all(ids_c[:, :-1][tie] < ids_c[:, 1:][tie])
+    return stats, ids, vals, keys
+
+
+@pytest.mark.parametrize("q,n,dim,k", [(48, 192, 640, 50), (1, 1, 64, 5), (7, 33, 100, 10), (130, 3000, 512, 51),
+                                       (257, 5000, 640, 100), (64, 2048, 64, 128), (65, 2049, 64, 128)])
+def test_fp32_validation_mode_matches_oracle(cuda_device, q, n, dim, k):
+    stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_FP32)
+    assert stats["exact_frac"] > 0.999
+
+
+@pytest.mark.parametrize("q,n,dim,k", [(48, 192, 640, 50), (100, 5000, 640, 100), (128, 2300, 512, 50),
+                                       (5, 130, 64, 10), (1, 4000, 640, 1)])
+def test_bf16_single_cta_matches_oracle(cuda_device, q, n, dim, k):
+    stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q <= 128 -> 1-CTA tcgen05 kernel
+    assert stats["exact_frac"] > 0.99
+
+
+@pytest.mark.parametrize("q,n,dim,k", [(300, 5000, 640, 100), (129, 257, 640, 50), (2017, 3817, 640, 51),
+                                       (512, 40000, 512, 100), (1000, 20000, 128, 128)])
+def test_bf16_cta_pair_matches_oracle(cuda_device, q, n, dim, k):
+    stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q > 128 -> cta_group::2 kernel
+    assert stats["exact_frac"] > 0.99
+
+
+def test_bf16_similarity_ranking_and_exclusion(cuda_device):
+    q, n = 200, 6000
+    ex = torch.randint(0, n, (q,), generator=torch.Generator().manual_seed(5))
+    ex[::7] = -1
+    run_case(cuda_device, q, n, 640, 50, MODE_BF16, rank_by=RANK_SIMILARITY, exclude=ex)
+    run_case(cuda_device, q, n, 640, 50, MODE_FP32, rank_by=RANK_REFERENCE, exclude=ex)
+
+
+def test_fewer_rows_than_k_pads(cuda_device):
+    pred, gal = unit(1, 9, 64).to(cuda_device), unit(2, 5, 64).to(cuda_device)
+    vals, ids, _, _ = ops.sim_topk(pred, gal, 8, mode=MODE_FP32)
+    assert bool((ids[:, 5:] == -1).all()) and bool(torch.isinf(vals[:, 5:]).all())
+    assert bool((ids[:, :5].sort(dim=1).values == torch.arange(5, device=cuda_device, dtype=torch.int32)).all())
+    vals, ids, _, _ = ops.sim_topk(pred.bfloat16(), gal.bfloat16(), 8, mode=MODE_BF16)
+    assert bool((ids[:, 5:] == -1).all())
+    v0, i0, _, _ = ops.sim_topk(pred, gal[:0], 4, mode=MODE_FP32)        # empty gallery
+    assert bool((i0 == -1).all())
+    v1, i1, _, _ = ops.sim_topk(pred[:0], gal, 4, mode=MODE_FP32)        # empty query batch
+    assert i1.shape == (0, 4)
+
+
+def test_duplicate_rows_tie_break_lowest_id(cuda_device):
+    g = unit(3, 40, 64)
+    gal = torch.cat([g, g, g])                     # every row three times -> exact ties
+    pred = unit(4, 6, 64)
+    for mode, cast in ((MODE_FP32, torch.float32), (MODE_BF16, torch.bfloat16)):
+        vals, ids, _, _ = ops.sim_topk(pred.to(cuda_device, cast), gal.to(cuda_device, cast), 9, mode=mode)
+        ids = ids.cpu().numpy()
+        assert np.all(ids[:, 0::3] + 40 == ids[:, 1::3]) and np.all(ids[:, 1::3] + 40 == ids[:, 2::3])
+
+
+def test_adversarial_order_overflows_then_falls_back_exactly(cuda_device):
+    # gallery sorted by increasing similarity to the query: every row beats the running threshold, the
+    # candidate list overflows, status[0] reports it and the conservative schedule restores exactness
+    n, dim = 30000, 64
+    base = unit(7, 1, dim)
+    noise = unit(8, n, dim)
+    w = torch.linspace(0.0, 1.0, n)[:, None]
+    gal = torch.nn.functional.normalize(w * base + (1 - w) * 0.3 * noise, dim=-1)
+    pred = base.repeat(3, 1)
+    qd, gd = pred.to(cuda_device), gal.to(cuda_device)
+    _, _, _, status = ops.sim_topk(qd, gd, 100, mode=MODE_FP32, check_overflow=False)
+    assert int(status[0].item()) > 0
+    vals, ids, _, status = ops.sim_topk(qd, gd, 100, mode=MODE_FP32, check_overflow=True)
+    assert int(status[0].item()) == 0
+    orc.compare_topk(ids.cpu().numpy(), None, pred, gal, 100, tol=TOL_FP32 + 1.2e-7)
+    _, ids_b, _, _ = ops.sim_topk(qd.bfloat16(), gd.bfloat16(), 100, mode=MODE_BF16)
+    orc.compare_topk(ids_b.cpu().numpy(), None, pred.bfloat16().float(), gal.bfloat16().float(), 100, tol=2e-6)
+
+
+def test_growth_schedules_agree(cuda_device):
+    q, n, k = 150, 50000, 100
+    pred, gal = unit(11, q, 128).bfloat16().to(cuda_device), unit(12, n, 128).bfloat16().to(cuda_device)
+    ref = ops.sim_topk(pred, gal, k)[1]
+    for growth in (1, 2, 4, 16):
+        assert torch.equal(ops.sim_topk(pred, gal, k, growth=growth)[1], ref)
+
+
+def test_shard_merge_equals_global(cuda_device):
+    q, n, k = 140, 9000, 100
+    pred, gal = unit(21, q, 640).bfloat16().to(cuda_device), unit(22, n, 640).bfloat16().to(cuda_device)
+    _, ids_all, keys_all, _ = ops.sim_topk(pred, gal, k, want_keys=True)
+    bounds = [0, 2250, 4500, 6750, 9000]
+    parts = [ops.sim_topk(pred, gal[a:b], k, id_offset=a, want_keys=True)[2] for a, b in zip(bounds[:-1], bounds[1:])]
+    vals, ids, keys = ops.topk_merge(torch.stack(parts), k)
+    assert torch.equal(ids, ids_all) and torch.equal(keys, keys_all)
+
+
+def test_recall_kernels_match_oracle(cuda_device):
+    q, n, k = 500, 4000, 50
+    pred, gal = unit(31, q, 640), unit(32, n, 640)
+    g = torch.Generator().manual_seed(33)
+    cls = torch.randint(0, 700, (n,), generator=g)            # non-unique classes (Fashion200k-style)
+    ids_o, _ = orc.rank_topk(pred, gal, k)
+    tgt_cls = cls[ids_o[torch.arange(q), syn.planted_ranks(34, q, 60).clamp(max=k - 1)]]
+    _, ids, _, _ = ops.sim_topk(pred.to(cuda_device), gal.to(cuda_device), k, mode=MODE_FP32)
+    counts, ranks = ops.recall_at_k(ids, cls.int().to(cuda_device), tgt_cls.int().to(cuda_device), (1, 10, 50))
+    exp_ranks = orc.first_hit_rank(ids.cpu().long(), cls.numpy(), tgt_cls.numpy())
+    assert np.array_equal(ranks.cpu().numpy(), exp_ranks)
+    assert counts.cpu().tolist() == [int((exp_ranks < kk).sum()) for kk in (1, 10, 50)]
+
+
+def test_large_gallery_bf16_subset_parity(cuda_device):
+    # 4096 x 1M x 640 (SURVEY.md 8d config 5 at its smallest size): parity on a 64-query subset against
+    # fp32 matmul + stable sort of the same bf16-rounded data (oracle), gap-aware
+    q, n, dim, k = 4096, 1_000_000, 640, 100
+    gen = torch.Generator(device=cuda_device).manual_seed(5000)
+    gal = torch.nn.functional.normalize(torch.randn(n, dim, generator=gen, device=cuda_device), dim=-1).bfloat16()
+    pred = torch.nn.functional.normalize(torch.randn(q, dim, generator=gen, device=cuda_device), dim=-1).bfloat16()
+    vals, ids, _, status = ops.sim_topk(pred, gal, k)
+    assert int(status[0].item()) == 0
+    sub = torch.arange(0, q, 64)
+    orc.compare_topk(ids[sub.to(cuda_device)].cpu().numpy(), None, pred[sub.to(cuda_device)].float().cpu(),
+                     gal.float().cpu(), k, tol=TOL_BF16_SAME_INPUTS)
