@@ -50,7 +50,8 @@ static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct SimWorkspace {
   uint64_t* lists;
-  int32_t* counts;
+  int32_t* prev_counts;
+  int32_t* seg_counts;
   float* thr;
   size_t bytes;
 };
@@ -60,8 +61,10 @@ static SimWorkspace carve_sim(void* base, int64_t nq) {
   size_t off = 0;
   w.lists = reinterpret_cast<uint64_t*>(p + off);
   off += align256(static_cast<size_t>(nq) * ERN_LIST_CAP * 8);
-  w.counts = reinterpret_cast<int32_t*>(p + off);
+  w.prev_counts = reinterpret_cast<int32_t*>(p + off);
   off += align256(static_cast<size_t>(nq) * 4);
+  w.seg_counts = reinterpret_cast<int32_t*>(p + off);
+  off += align256(static_cast<size_t>(nq) * ERN_MAX_CHUNKS * 4);
   w.thr = reinterpret_cast<float*>(p + off);
   off += align256(static_cast<size_t>(nq) * 4);
   w.bytes = off;
@@ -218,40 +221,44 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
     }
   }
 
-  rc = launch_init_state(ws.counts, ws.thr, nq, status_dev, st);
+  rc = launch_init_state(ws.prev_counts, ws.seg_counts, ws.thr, nq, status_dev, st);
   if (rc) return rc;
 
   CandidateSink sink;
+  memset(&sink, 0, sizeof(sink));
   sink.lists = ws.lists;
-  sink.counts = ws.counts;
+  sink.seg_counts = ws.seg_counts;
   sink.thresholds = ws.thr;
   sink.exclude = exclude_id_dev;
   sink.status = status_dev;
   sink.cap = ERN_LIST_CAP;
+  sink.keep = k;
   sink.id_offset = id_offset;
   sink.nq = nq;
 
   SelectParams sp;
   memset(&sp, 0, sizeof(sp));
-  sp.src = ws.lists;
-  sp.query_stride = ERN_LIST_CAP;
-  sp.n_lists = 1;
+  sp.lists = ws.lists;
   sp.cap = ERN_LIST_CAP;
+  sp.keep = k;
+  sp.prev_counts = ws.prev_counts;
+  sp.seg_counts = ws.seg_counts;
   sp.k = k;
-  sp.list_out = ws.lists;
-  sp.out_stride = ERN_LIST_CAP;
-  sp.counts_out = ws.counts;
   sp.thresholds = ws.thr;
   sp.status = status_dev;
 
+  // Threshold schedule.  Launch 0 keeps every score of the first ERN_DENSE_ROWS rows; each later launch
+  // covers rows [b, growth*b) with the threshold fixed at the exact k-th best of rows [0, b): the expected
+  // number of survivors per query and launch is (growth-1)*k, independent of the gallery size.
+  // growth == 1: fixed steps of ERN_SORT_CAP - k rows written by a single chunk -- cannot overflow.
   int64_t begin = 0;
   bool first = true;
   do {
     int64_t end;
     if (first) {
-      end = n_rows < ERN_LIST_CAP ? n_rows : ERN_LIST_CAP;
+      end = ERN_DENSE_ROWS;
     } else if (growth == 1) {
-      end = begin + (ERN_LIST_CAP - k);  // at most cap - k appends on top of k kept entries: cannot overflow
+      end = begin + (ERN_SORT_CAP - k);
     } else {
       end = begin * growth;
     }
@@ -259,17 +266,23 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
     sink.dense = first ? 1 : 0;
     sink.row_begin = begin;
     sink.row_end = end;
+    sink.n_chunks = (growth == 1) ? 1 : ERN_MAX_CHUNKS;   // upper bound; the launcher picks the actual split
+    sink.seg_size = (sink.cap - sink.keep) / sink.n_chunks;
     if (end > begin) {
-      if (mode == ERN_MODE_FP32)
+      if (mode == ERN_MODE_FP32) {
+        sink.n_chunks = 1;
+        sink.seg_size = sink.cap - sink.keep;
         rc = simf32::launch(static_cast<const float*>(queries_dev), ldq, static_cast<const float*>(gallery_dev), ldg,
                             dim, sink, rank_by, st);
-      else
+      } else {
         rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, st);
+      }
       if (rc) return rc;
     }
     const bool last = end >= n_rows;
-    sp.counts_in = first ? nullptr : ws.counts;
-    sp.dense_count = static_cast<int>(end - begin);
+    sp.dense_count = first ? static_cast<int>(end - begin) : 0;
+    sp.n_chunks = first ? 0 : sink.n_chunks;
+    sp.seg_size = sink.seg_size;
     sp.out_scores = last ? out_scores_dev : nullptr;
     sp.out_ids = last ? out_ids_dev : nullptr;
     sp.out_keys = last ? out_keys_dev : nullptr;
@@ -288,17 +301,15 @@ int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, 
   int rc = current_device(&di);
   if (rc) return rc;
   ERN_REQUIRE(keys_dev && nq >= 0 && n_lists >= 1 && k_in >= 1, "bad arguments");
-  ERN_REQUIRE(static_cast<int64_t>(n_lists) * k_in <= ERN_LIST_CAP, "n_lists * k_in must be <= %d", ERN_LIST_CAP);
+  ERN_REQUIRE(static_cast<int64_t>(n_lists) * k_in <= ERN_SORT_CAP, "n_lists * k_in must be <= %d", ERN_SORT_CAP);
   ERN_REQUIRE(k_out >= 1 && k_out <= ERN_MAX_K, "k_out must be in [1,%d]", ERN_MAX_K);
   SelectParams sp;
   memset(&sp, 0, sizeof(sp));
-  sp.src = keys_dev;
+  sp.merge_src = keys_dev;
   sp.list_stride = list_stride;
   sp.query_stride = query_stride;
   sp.n_lists = n_lists;
   sp.k_in = k_in;
-  sp.dense_count = k_in;
-  sp.cap = ERN_LIST_CAP;
   sp.k = k_out;
   sp.out_scores = out_scores_dev;
   sp.out_ids = out_ids_dev;

@@ -68,32 +68,42 @@ __device__ __forceinline__ float rank_value(float s) {
 }
 
 // ---- candidate sink: where the scoring kernels put (value, id) pairs that pass the threshold --------
+// One list of `cap` 64-bit slots per query.  Slots [0, keep) hold the survivors of earlier launches.  The rest
+// is cut into `n_chunks` segments of `seg_size` slots; a segment has exactly one writer (the work item that
+// scores gallery chunk c for this query), which appends with a private register counter -- no atomics on the
+// hot path -- and publishes its count in seg_counts[q, c] when it finishes.  The fp32 validation kernel, whose
+// blocks are not aligned with chunks, uses a single segment with an atomic cursor in seg_counts[q, 0].
 struct CandidateSink {
-  uint64_t* lists;        // [nq, cap]
-  int32_t* counts;        // [nq]   appended entries per query (filter mode)
+  uint64_t* lists;          // [nq, cap]
+  int32_t* seg_counts;      // [nq, ERN_MAX_CHUNKS]
   const float* thresholds;  // [nq] current lower bound on the k-th best ranking value (-inf at start)
   const int32_t* exclude;   // [nq] global id to drop, or nullptr
-  int32_t* status;        // [4]
+  int32_t* status;          // [4]
   int cap;
-  int dense;              // 1: every row of [row_begin,row_end) is stored at slot (row - row_begin)
-  int64_t row_begin;      // shard-local gallery rows covered by this launch
+  int keep;
+  int n_chunks;
+  int seg_size;
+  int dense;                // 1: every row of [row_begin,row_end) is stored at slot (row - row_begin)
+  int64_t row_begin;        // shard-local gallery rows covered by this launch
   int64_t row_end;
-  int64_t id_offset;      // global id of shard row 0
+  int64_t id_offset;        // global id of shard row 0
   int64_t nq;
 };
 
-// Append one candidate for query q (caller guarantees q < nq, row in [row_begin,row_end)).
-__device__ __forceinline__ void sink_put(const CandidateSink& s, int64_t q, int64_t row, float value,
-                                         int32_t excl) {
+// dense launches: slot = row - row_begin, NaN scores and the excluded id become empty slots
+__device__ __forceinline__ void sink_put_dense(const CandidateSink& s, int64_t q, int64_t row, float value,
+                                               int32_t excl) {
   const uint32_t gid = static_cast<uint32_t>(row + s.id_offset);
-  if (s.dense) {
-    const bool drop = (static_cast<int32_t>(gid) == excl) || !(value == value);
-    s.lists[q * s.cap + (row - s.row_begin)] = drop ? 0ull : make_key(value, gid);
-  } else {
-    if (static_cast<int32_t>(gid) == excl) return;
-    const int pos = atomicAdd(&s.counts[q], 1);
-    if (pos < s.cap) s.lists[q * s.cap + pos] = make_key(value, gid);
-  }
+  const bool drop = (static_cast<int32_t>(gid) == excl) || !(value == value);
+  s.lists[q * s.cap + (row - s.row_begin)] = drop ? 0ull : make_key(value, gid);
+}
+// single-segment atomic append (fp32 validation kernel only)
+__device__ __forceinline__ void sink_put_atomic(const CandidateSink& s, int64_t q, int64_t row, float value,
+                                                int32_t excl) {
+  const uint32_t gid = static_cast<uint32_t>(row + s.id_offset);
+  if (static_cast<int32_t>(gid) == excl) return;
+  const int pos = atomicAdd(&s.seg_counts[q * ERN_MAX_CHUNKS], 1);
+  if (pos < s.seg_size) s.lists[q * s.cap + s.keep + pos] = make_key(value, gid);
 }
 
 // ---- launch-plan helpers shared by the C ABI ---------------------------------------------------------

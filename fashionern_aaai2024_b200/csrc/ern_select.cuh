@@ -3,24 +3,27 @@
 #include "ern_common.cuh"
 namespace ern {
 struct SelectParams {
-  // source: either `n_lists` segments (merge) or the query's own list with `counts` / dense_count
-  const uint64_t* src;
-  int64_t list_stride;   // between segments of one query (merge), unused otherwise
-  int64_t query_stride;  // between queries
+  // ---- source A (merge): `n_lists` > 0 segments of k_in keys per query, laid out with the two strides
+  const uint64_t* merge_src;
+  int64_t list_stride;
+  int64_t query_stride;
   int n_lists;
-  int k_in;              // entries per segment (merge)
-  const int32_t* counts_in;  // nullable: per query number of valid entries in src (filter mode)
-  int dense_count;       // entries per query when counts_in == nullptr && n_lists == 1
+  int k_in;
+  // ---- source B (a query's own candidate list, see CandidateSink)
+  uint64_t* lists;           // [nq, cap]; the compacted top-k is written back to slots [0,k)
   int cap;
+  int keep;                  // survivors of earlier launches live in slots [0, prev_counts[q])
+  int32_t* prev_counts;      // [nq]  in: survivors, out: min(n, k)
+  int32_t* seg_counts;       // [nq, ERN_MAX_CHUNKS]; reset to 0 after reading
+  int n_chunks;
+  int seg_size;
+  int dense_count;           // > 0: slots [0, dense_count) are all candidates (first launch), segments unused
   int k;
-  // outputs (all nullable)
-  uint64_t* list_out;    // [nq, out_stride] compacted list written back (first k entries)
-  int64_t out_stride;
-  int32_t* counts_out;   // [nq]
-  float* thresholds;     // [nq]
-  float* out_scores;     // [nq, k]
-  int32_t* out_ids;      // [nq, k]
-  uint64_t* out_keys;    // [nq, k]
+  // ---- outputs (nullable)
+  float* thresholds;         // [nq]
+  float* out_scores;         // [nq, k]
+  int32_t* out_ids;          // [nq, k]
+  uint64_t* out_keys;        // [nq, k]
   int32_t* status;
 };
 }  // namespace ern

@@ -64,7 +64,8 @@ sim_f32_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict
       const int64_t row = g0 + tx * 4 + j;
       if (row >= sink.row_end) continue;
       const float r = rank_value<kRankBy>(acc[i][j]);
-      if (sink.dense || r >= thr) sink_put(sink, q, row, r, excl);
+      if (sink.dense) sink_put_dense(sink, q, row, r, excl);
+      else if (r >= thr) sink_put_atomic(sink, q, row, r, excl);
     }
   }
 }

@@ -36,6 +36,7 @@ struct Params {
   int tiles_total;      // gallery tiles of TILE_G rows in [row_begin, row_end)
   int tiles_per_chunk;
   int n_chunks;
+  int debug;            // profiling aid (ERN_DEBUG_FLAGS): 1 = never take the append path, 2 = skip the TMEM reads
 };
 
 struct Barriers {
@@ -175,8 +176,12 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const int chunk = item / p.n_qtiles;
       const int64_t q = static_cast<int64_t>(qt) * (kBlockQ * kCta) + rank * kBlockQ + row_in_tile;
       const bool q_ok = q < sink.nq;
-      const float thr = q_ok ? (sink.dense ? -INFINITY : sink.thresholds[q]) : INFINITY;
+      const bool dense = sink.dense != 0;
+      const float thr = q_ok ? (dense ? -INFINITY : sink.thresholds[q]) : INFINITY;
       const int32_t excl = (q_ok && sink.exclude) ? sink.exclude[q] : -1;
+      // this thread is the only writer of segment `chunk` of query q: private cursor, plain stores
+      uint64_t* seg = sink.lists + (q_ok ? q : 0) * sink.cap + sink.keep + static_cast<int64_t>(chunk) * sink.seg_size;
+      int cnt = 0;
       const int t0 = chunk * p.tiles_per_chunk;
       const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
       for (int t = t0; t < t1; ++t) {
@@ -185,24 +190,41 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int64_t g_base = sink.row_begin + static_cast<int64_t>(t) * kTileG;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
         uint32_t v[2][32];
+        if (!(p.debug & 2)) {
         ptx::tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
         for (int c = 0; c < kAccCols / 32; ++c) {
           ptx::tmem_ld_wait();
           if (c + 1 < kAccCols / 32) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
           const uint32_t(&cur)[32] = v[c & 1];
-          float m = __uint_as_float(cur[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(cur[j]));
-          // dense launches store every row (NaN scores become empty slots), filter launches only survivors
-          if (sink.dense || rank_value<kRankBy>(m) >= thr) {
+          if (dense) {
+            // every row is kept (NaN scores / the excluded id become empty slots)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float r = rank_value<kRankBy>(__uint_as_float(cur[j]));
               const int64_t row = g_base + c * 32 + j;
-              if ((sink.dense || r >= thr) && row < sink.row_end && q_ok) sink_put(sink, q, row, r, excl);
+              if (row < sink.row_end && q_ok)
+                sink_put_dense(sink, q, row, rank_value<kRankBy>(__uint_as_float(cur[j])), excl);
+            }
+          } else {
+            float m = __uint_as_float(cur[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(cur[j]));
+            if (rank_value<kRankBy>(m) >= thr && !(p.debug & 1)) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float r = rank_value<kRankBy>(__uint_as_float(cur[j]));
+                const int64_t row = g_base + c * 32 + j;
+                if (r >= thr && row < sink.row_end && q_ok) {
+                  const uint32_t gid = static_cast<uint32_t>(row + sink.id_offset);
+                  if (static_cast<int32_t>(gid) != excl) {
+                    if (cnt < sink.seg_size) seg[cnt] = make_key(r, gid);
+                    ++cnt;
+                  }
+                }
+              }
             }
           }
+        }
         }
         // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
         ptx::tc_fence_before();
@@ -213,6 +235,9 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      // publish how many candidates this work item left in its segment (may exceed seg_size: the selection
+      // kernel reports that as an overflow)
+      if (q_ok && !dense) sink.seg_counts[q * ERN_MAX_CHUNKS + chunk] = cnt;
     }
   }
 
@@ -292,10 +317,10 @@ static int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const Params
 
 // Pick the chunking of [row_begin,row_end) that minimises the modelled makespan: items = qtiles x chunks are
 // dealt round-robin to the persistent units; every item pays one extra tile-time to (re)load its query tile.
-static void plan_chunks(int n_qtiles, int tiles_total, int units, int* n_chunks, int* tiles_per_chunk) {
+static void plan_chunks(int n_qtiles, int tiles_total, int units, int max_chunks, int* n_chunks, int* tiles_per_chunk) {
   long best_cost = -1;
   int best_c = 1;
-  const int cmax = tiles_total < 8192 ? tiles_total : 8192;
+  const int cmax = tiles_total < max_chunks ? tiles_total : max_chunks;
   for (int c = 1; c <= cmax; ++c) {
     const long tpc = (tiles_total + c - 1) / c;
     const long real_c = (tiles_total + tpc - 1) / tpc;
@@ -311,18 +336,25 @@ static void plan_chunks(int n_qtiles, int tiles_total, int units, int* n_chunks,
 }
 
 // One launch of the tensor-core scoring kernel over shard rows [sink.row_begin, sink.row_end).
-int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
+int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, int dim, int rank_by,
            int force_single, int sm_count, cudaStream_t st) {
   const bool pair = !force_single && sink.nq > kBlockQ;
   const int tile_g = pair ? 256 : 128;
   Params p;
-  p.sink = sink;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("ERN_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
   p.num_kblocks = dim / kBlockK;
   p.n_qtiles = cdiv(sink.nq, pair ? 2 * kBlockQ : kBlockQ);
   p.tiles_total = cdiv(sink.row_end - sink.row_begin, tile_g);
   if (p.tiles_total <= 0) return ERN_OK;
   int units = pair ? sm_count / 2 : sm_count;
-  plan_chunks(p.n_qtiles, p.tiles_total, units, &p.n_chunks, &p.tiles_per_chunk);
+  // on entry sink.n_chunks is the caller's upper bound on chunks (1 for the overflow-proof schedule)
+  const int max_chunks = sink.n_chunks > 0 && sink.n_chunks < ERN_MAX_CHUNKS ? sink.n_chunks : ERN_MAX_CHUNKS;
+  plan_chunks(p.n_qtiles, p.tiles_total, units, max_chunks, &p.n_chunks, &p.tiles_per_chunk);
+  sink.n_chunks = p.n_chunks;
+  sink.seg_size = (sink.cap - sink.keep) / p.n_chunks;
+  p.sink = sink;
   const long items = static_cast<long>(p.n_qtiles) * p.n_chunks;
   if (items < units) units = static_cast<int>(items);
   const int grid = pair ? 2 * units : units;

@@ -14,33 +14,55 @@ constexpr int kSelectThreads = 256;
 
 
 __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const SelectParams p) {
-  __shared__ uint64_t keys[ERN_LIST_CAP];
+  __shared__ uint64_t keys[ERN_SORT_CAP];
+  __shared__ int n_shared;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
+  if (tid == 0) n_shared = 0;
+  __syncthreads();
 
-  int n;
-  if (p.n_lists > 1 || p.counts_in == nullptr) {
-    n = (p.n_lists > 1) ? p.n_lists * p.k_in : p.dense_count;
+  // ---- gather the non-empty candidates densely into shared memory (order is irrelevant: they get sorted)
+  auto push = [&](uint64_t key) {
+    if (key != 0ull) {
+      const int pos = atomicAdd(&n_shared, 1);
+      if (pos < ERN_SORT_CAP) keys[pos] = key;
+    }
+  };
+  if (p.n_lists > 0) {
+    const int total = p.n_lists * p.k_in;
+    for (int i = tid; i < total; i += kSelectThreads)
+      push(p.merge_src[(i / p.k_in) * p.list_stride + q * p.query_stride + (i % p.k_in)]);
   } else {
-    const int c = p.counts_in[q];
-    if (c > p.cap && tid == 0 && p.status) atomicAdd(&p.status[0], 1);
-    n = c < p.cap ? c : p.cap;
+    const uint64_t* list = p.lists + q * p.cap;
+    if (p.dense_count > 0) {
+      for (int i = tid; i < p.dense_count; i += kSelectThreads) push(list[i]);
+    } else {
+      const int prev = p.prev_counts[q];
+      for (int i = tid; i < prev; i += kSelectThreads) push(list[i]);
+      const int span = p.n_chunks * p.seg_size;
+      int32_t* sc = p.seg_counts + q * ERN_MAX_CHUNKS;
+      for (int i = tid; i < span; i += kSelectThreads) {
+        const int c = i / p.seg_size, off = i - c * p.seg_size;
+        if (off < sc[c]) push(list[p.keep + i]);
+      }
+      __syncthreads();
+      if (tid < p.n_chunks) {
+        if (sc[tid] > p.seg_size && p.status) atomicAdd(&p.status[0], 1);   // a segment overflowed: not exact
+        sc[tid] = 0;
+      }
+    }
+  }
+  __syncthreads();
+  int n = n_shared;
+  if (n > ERN_SORT_CAP) {
+    if (tid == 0 && p.status) atomicAdd(&p.status[0], 1);
+    n = ERN_SORT_CAP;
   }
   int pow2 = 32;
   while (pow2 < n) pow2 <<= 1;
+  for (int i = n + tid; i < pow2; i += kSelectThreads) keys[i] = 0ull;
 
-  if (p.n_lists > 1) {
-    for (int i = tid; i < pow2; i += kSelectThreads) {
-      uint64_t v = 0;
-      if (i < n) v = p.src[(i / p.k_in) * p.list_stride + q * p.query_stride + (i % p.k_in)];
-      keys[i] = v;
-    }
-  } else {
-    const uint64_t* src = p.src + q * p.query_stride;
-    for (int i = tid; i < pow2; i += kSelectThreads) keys[i] = i < n ? src[i] : 0ull;
-  }
-
-  // bitonic sort, descending
+  // ---- bitonic sort, descending
   for (int size = 2; size <= pow2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncthreads();
@@ -61,16 +83,15 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
   const int k = p.k;
   for (int j = tid; j < k; j += kSelectThreads) {
     const uint64_t key = (j < pow2) ? keys[j] : 0ull;
-    if (p.list_out) p.list_out[q * p.out_stride + j] = key;
+    if (p.lists) p.lists[q * p.cap + j] = key;
     if (p.out_keys) p.out_keys[q * k + j] = key;
     if (p.out_scores) p.out_scores[q * k + j] = key ? key_value(key) : -INFINITY;
     if (p.out_ids) p.out_ids[q * k + j] = key ? key_id(key) : -1;
   }
   if (tid == 0) {
     const uint64_t kth = (k - 1 < pow2) ? keys[k - 1] : 0ull;
-    int valid = n < k ? n : k;
-    if (p.counts_out) p.counts_out[q] = valid;
-    // a key of 0 inside the first k means fewer than k real candidates so far: no lower bound yet
+    if (p.prev_counts) p.prev_counts[q] = n < k ? n : k;
+    // fewer than k real candidates so far: no lower bound yet
     if (p.thresholds) p.thresholds[q] = kth ? key_value(kth) : -INFINITY;
   }
 }
@@ -82,18 +103,20 @@ int launch_select(const SelectParams& p, int64_t nq, cudaStream_t st) {
   return ERN_OK;
 }
 
-__global__ void init_state_kernel(int32_t* counts, float* thr, int64_t nq, int32_t* status) {
+__global__ void init_state_kernel(int32_t* prev_counts, int32_t* seg_counts, float* thr, int64_t nq, int32_t* status) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < nq) {
-    counts[i] = 0;
+    prev_counts[i] = 0;
     thr[i] = -INFINITY;
   }
+  if (i < nq * ERN_MAX_CHUNKS) seg_counts[i] = 0;
   if (i < 4 && status) status[i] = 0;
 }
 
-int launch_init_state(int32_t* counts, float* thr, int64_t nq, int32_t* status, cudaStream_t st) {
-  const int64_t n = nq < 4 ? 4 : nq;
-  init_state_kernel<<<cdiv(n, 256), 256, 0, st>>>(counts, thr, nq, status);
+int launch_init_state(int32_t* prev_counts, int32_t* seg_counts, float* thr, int64_t nq, int32_t* status,
+                      cudaStream_t st) {
+  const int64_t n = nq * ERN_MAX_CHUNKS < 4 ? 4 : nq * ERN_MAX_CHUNKS;
+  init_state_kernel<<<cdiv(n, 256), 256, 0, st>>>(prev_counts, seg_counts, thr, nq, status);
   ERN_CUDA(cudaGetLastError());
   return ERN_OK;
 }

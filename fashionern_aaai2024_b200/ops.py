@@ -11,8 +11,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (DTYPE_BF16, DTYPE_F32, LIST_CAP, MAX_K, MODE_BF16, MODE_FP32, RANK_REFERENCE,
-                   RANK_SIMILARITY, ErnError)
+from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MAX_K, MODE_BF16, MODE_FP32, RANK_REFERENCE,
+                   RANK_SIMILARITY, SORT_CAP, ErnError)
 
 __all__ = ["l2norm_rows", "sim_topk", "topk_merge", "recall_at_k", "cirr_subset_recall", "launch_counter"]
 
@@ -61,11 +61,10 @@ def l2norm_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, 
 
 
 def _phase_count(n_rows: int, k: int, growth: int) -> int:
-    if n_rows <= LIST_CAP:
-        return 1
-    n, begin = 1, LIST_CAP
+    """Number of scoring launches ern_sim_topk issues (mirrors the schedule in csrc/ern_capi.cu)."""
+    n, begin = 1, min(n_rows, DENSE_ROWS)
     while begin < n_rows:
-        begin = begin + (LIST_CAP - k) if growth == 1 else begin * growth
+        begin = begin + (SORT_CAP - k) if growth == 1 else begin * growth
         n += 1
     return n
 
@@ -112,6 +111,9 @@ def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int 
                                      ws.data_ptr(), wsb, L.stream_ptr(dev)))
             launch_counter.add(1 + 2 * _phase_count(n_rows, k, gr) if nq else 0)
 
+        if nq == 0:
+            status.zero_()
+            return vals, ids, keys, status
         run(growth)
         if check_overflow and nq and int(status[0].item()) != 0:
             run(1)

@@ -44,7 +44,7 @@ def combiner_state(seed: int, dim: int, scale: float = 1.0) -> Dict[str, torch.T
     sd["text_projection_layer.0.weight"], sd["text_projection_layer.0.bias"] = lin(proj, dim)
     sd["image_projection_layer.0.weight"], sd["image_projection_layer.0.bias"] = lin(proj, dim)
     # make the gate informative: default init gives |logit| << 1, i.e. s ~ 0.5 everywhere
-    sd["dynamic_scalar.3.weight"] = sd["dynamic_scalar.3.weight"] * 40.0
+    sd["dynamic_scalar.3.weight"] = sd["dynamic_scalar.3.weight"] * 10.0
     return sd
 
 

@@ -54,9 +54,14 @@ extern "C" {
 #define ERN_RANK_REFERENCE 1  /* -(1 - s) rounded in fp32: the reference's `1 - pred @ index.T`    */
                               /* (run/test/test_fiq.py:49) with its rounding-induced ties          */
 
-/* max k of the streaming top-k, and per-query capacity of the candidate list */
+/* max k of the streaming top-k; slots of one query's candidate list; max candidates one selection/merge
+ * pass can take; max gallery chunks (= independent writers) per query and launch */
 #define ERN_MAX_K 128
-#define ERN_LIST_CAP 2048
+#define ERN_LIST_CAP 4096
+#define ERN_SORT_CAP 2048
+#define ERN_MAX_CHUNKS 64
+/* gallery rows scored densely (every score kept) before thresholds exist */
+#define ERN_DENSE_ROWS 256
 
 ERN_API int ern_version(void);
 ERN_API const char* ern_last_error(void);
@@ -132,7 +137,7 @@ ERN_API int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const
 /* ---------------------------------------------------------------------------------------------
  * k-way merge of per-shard / per-rank candidate lists (after the NCCL all-gather of keys):
  * list l of query q starts at keys_dev + l*list_stride + q*query_stride and holds k_in keys.
- * n_lists * k_in <= ERN_LIST_CAP.
+ * n_lists * k_in <= ERN_SORT_CAP.
  * ------------------------------------------------------------------------------------------- */
 ERN_API int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, int64_t list_stride,
                    int64_t query_stride, int k_out, float* out_scores_dev, int32_t* out_ids_dev,

@@ -50,7 +50,7 @@ def test_ragged_batches_against_oracle(cuda_device, rows, mode):
     err = (out.cpu() - ref).norm(dim=-1)
     assert float(err.max()) <= tol
     assert float((out_b.float().cpu() - out.cpu()).abs().max()) <= 2 ** -8      # bf16 rounding of unit vectors
-    assert 0.02 < float(gate.min()) and float(gate.max()) < 0.98 or rows == 1   # the synthetic gate is informative
+    assert rows < 100 or float(gate.max() - gate.min()) > 0.2                    # the synthetic gate is informative
 
 
 def test_dvr_call_site_inputs(cuda_device):

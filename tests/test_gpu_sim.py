@@ -48,7 +48,7 @@ def run_case(dev, q, n, dim, k, mode, rank_by=RANK_REFERENCE, exclude=None, grow
 
 
 @pytest.mark.parametrize("q,n,dim,k", [(48, 192, 640, 50), (1, 1, 64, 5), (7, 33, 100, 10), (130, 3000, 512, 51),
-                                       (257, 5000, 640, 100), (64, 2048, 64, 128), (65, 2049, 64, 128)])
+                                       (257, 5000, 640, 100), (64, 2048, 64, 128), (65, 2049, 64, 128), (33, 256, 64, 128), (33, 257, 64, 128)])
 def test_fp32_validation_mode_matches_oracle(cuda_device, q, n, dim, k):
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_FP32)
     assert stats["exact_frac"] > 0.999
