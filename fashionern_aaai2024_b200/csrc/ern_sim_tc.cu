@@ -189,34 +189,49 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         ptx::tc_fence_after();
         const int64_t g_base = sink.row_begin + static_cast<int64_t>(t) * kTileG;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
-        uint32_t v[2][32];
         if (!(p.debug & 2)) {
-        ptx::tmem_ld_32x32(taddr, v[0]);
-#pragma unroll
-        for (int c = 0; c < kAccCols / 32; ++c) {
-          ptx::tmem_ld_wait();
-          if (c + 1 < kAccCols / 32) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-          const uint32_t(&cur)[32] = v[c & 1];
-          if (dense) {
-            // every row is kept (NaN scores / the excluded id become empty slots)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t row = g_base + c * 32 + j;
-              if (row < sink.row_end && q_ok)
-                sink_put_dense(sink, q, row, rank_value<kRankBy>(__uint_as_float(cur[j])), excl);
-            }
-          } else {
-            float m = __uint_as_float(cur[0]);
-#pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(cur[j]));
-            if (rank_value<kRankBy>(m) >= thr && !(p.debug & 1)) {
+          // The chunk loop is deliberately NOT unrolled and the survivor path is a bit-mask walk: the whole
+          // epilogue stays a few KB of code.  (A fully unrolled version was 250 KB and ran from L2 instruction
+          // fetches: ncu showed stall_no_inst on every epilogue instruction and 6% tensor-pipe activity.)
+#pragma unroll 1
+          for (int c = 0; c < kAccCols / 32; ++c) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + c * 32, v);
+            ptx::tmem_ld_wait();
+            const int64_t row0 = g_base + c * 32;
+            if (dense) {
+              // every row is kept (NaN scores / the excluded id become empty slots)
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const float r = rank_value<kRankBy>(__uint_as_float(cur[j]));
-                const int64_t row = g_base + c * 32 + j;
-                if (r >= thr && row < sink.row_end && q_ok) {
+                if (row0 + j < sink.row_end && q_ok)
+                  sink_put_dense(sink, q, row0 + j, rank_value<kRankBy>(__uint_as_float(v[j])), excl);
+              }
+            } else {
+              float m = __uint_as_float(v[0]);
+#pragma unroll
+              for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+              if (rank_value<kRankBy>(m) >= thr && !(p.debug & 1)) {
+                uint32_t mask = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  mask |= (rank_value<kRankBy>(__uint_as_float(v[j])) >= thr ? 1u : 0u) << j;
+                while (mask) {
+                  const int j = __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  // register file has no dynamic indexing: 5-level select tree picks v[j]
+                  uint32_t s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) s16[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) s8[i] = (j & 8) ? s16[i + 8] : s16[i];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[i + 4] : s8[i];
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) s2[i] = (j & 2) ? s4[i + 2] : s4[i];
+                  const float r = rank_value<kRankBy>(__uint_as_float((j & 1) ? s2[1] : s2[0]));
+                  const int64_t row = row0 + j;
                   const uint32_t gid = static_cast<uint32_t>(row + sink.id_offset);
-                  if (static_cast<int32_t>(gid) != excl) {
+                  if (row < sink.row_end && q_ok && static_cast<int32_t>(gid) != excl) {
                     if (cnt < sink.seg_size) seg[cnt] = make_key(r, gid);
                     ++cnt;
                   }
@@ -224,7 +239,6 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               }
             }
           }
-        }
         }
         // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
         ptx::tc_fence_before();
