@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Headline benchmark of the composed-retrieval scoring path (BASELINE.json: queries/sec, top-100, 640-d,
+synthetic gallery, 4096-query batches, gallery row-sharded over N B200s of one box).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                       # ours, N = 1 (default)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                            # ours, N ranks over NCCL
+    python bench.py --impl reference ...                                  # the reference's CPU path (oracle port)
+
+One STEP = one batch of 4096 composed queries through the whole hot path:
+    fusion head (CombinerSimple: image+text CLIP features -> unit-norm query, tcgen05 GEMMs)
+ -> bf16 cosine scoring of the batch against this rank's gallery shard with streaming top-100 (tcgen05)
+ -> [N > 1] NCCL all-gather of the (score,id) candidate keys + device k-way merge
+ -> Recall@{1,10,50,100} hit counts from id membership on device.
+`value`  : queries/s of the whole job with every input already resident in HBM (CUDA events, max over ranks).
+`e2e`    : same metric through the public API with HOST inputs: per step the query batch's image/text features
+           and target ids are copied from pinned host memory, and the top-k ids/scores + hit counts are read back.
+The gallery (rows x 640 bf16 = 128 GB at 100M rows) is far larger than L2 (126 MB), so every step streams it
+from HBM: no L2 flush is needed between timed iterations (stated in `config.l2`).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KS = (1, 10, 50, 100)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gallery-rows", type=int, default=100_000_000, help="total gallery rows over all ranks")
+    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--dim", type=int, default=640)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--cpu-sample-queries", type=int, default=128)
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_sustained": float(p.get("bf16_tflops_sustained", 1400.0)), "bf16_burst": float(p.get("bf16_tflops", 1590.0)),
+                "hbm": float(p.get("hbm_gbs", 6650.0)), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's torch CPU path (oracle port), bounded sample
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_qps(args, steps=1, warmup=0):
+    """fp32 `1 - q @ G.T` + FULL torch.argsort + first-k + id-membership recall (run/test/test_fiq.py:49-60) on the
+    host cores, on a bounded sample (sq queries x sn gallery rows), scaled linearly in N to the benched gallery."""
+    from oracle import ern_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    sq, sn = args.cpu_sample_queries, min(args.cpu_sample_rows, args.gallery_rows)
+    g = torch.Generator().manual_seed(5000)
+    gal = torch.nn.functional.normalize(torch.randn(sn, args.dim, generator=g), dim=-1)
+    pred = torch.nn.functional.normalize(torch.randn(sq, args.dim, generator=g), dim=-1)
+    tgt = torch.randint(0, sn, (sq,), generator=g).numpy()
+    cls = torch.arange(sn).numpy()
+    from fashionern_aaai2024_b200 import synthetic as syn
+    sd = syn.combiner_state(7, args.dim)
+    img, txt = syn.features(8, sq, args.dim), syn.features(9, sq, args.dim)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            _ = orc.combiner_forward(sd, img, txt)                     # models/fusion_model.py:86-94 (query fusion)
+        d = orc.distances(pred, gal)                                   # :49
+        order = torch.argsort(d, dim=-1)                               # :50 (full sort, as the reference does)
+        ranks = orc.first_hit_rank(order[:, :args.k], cls, tgt)        # :51-55 restated on ids
+        _ = orc.recall_at(ranks, KS)                                   # :59-60
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    qps_sample = sq / t
+    qps = qps_sample * sn / args.gallery_rows
+    return qps, t, {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"{sq} queries x {sn} gallery rows x {args.dim}-d fp32, 1 - q@G.T + full argsort + recall "
+                              f"({t:.2f} s per pass = {qps_sample:.1f} q/s on the sample), scaled linearly in N to "
+                              f"{args.gallery_rows} rows"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    qps, t, cb = cpu_reference_qps(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    print(json.dumps({
+        "impl": "reference", "metric": "queries/sec (top-100, 640-d)", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": args.queries / qps * 1e3, "sample_pass_ms": t * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus), "cpu_baseline": cb,
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic gallery {args.gallery_rows} rows x {args.dim}-d bf16 (unit-norm, seeded on device), "
+                        f"{args.queries}-query batches, top-{args.k}, Recall@{list(KS)}",
+            "gallery_rows": args.gallery_rows, "queries_per_step": args.queries, "dim": args.dim, "k": args.k,
+            "parallelism": f"gallery row-sharded over {world} GPU(s), queries replicated",
+            "l2": "gallery shard >> 126 MB L2, streamed from HBM every step (no flush needed)"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import fashionern_aaai2024_b200 as ern
+    from fashionern_aaai2024_b200 import ops, sharded, synthetic as syn
+    from fashionern_aaai2024_b200.combiner import CombinerSimple
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ern._lib.require_device(dev)
+
+    Q, D, K, N = args.queries, args.dim, args.k, args.gallery_rows
+    begin, end = sharded.shard_bounds(N, world, rank)
+    rows = end - begin
+
+    # ---- gallery shard, generated on the device in row blocks ------------------------
+    gen = torch.Generator(device=dev).manual_seed(5000 + rank)
+    gallery = torch.empty((rows, D), dtype=torch.bfloat16, device=dev)
+    blk = 1 << 20
+    for s in range(0, rows, blk):
+        x = torch.randn(min(blk, rows - s), D, generator=gen, device=dev)
+        gallery[s:s + blk] = torch.nn.functional.normalize(x, dim=-1).bfloat16()
+    del x
+    class_of = torch.arange(N, dtype=torch.int32, device=dev)          # unique names: class id == global row id
+
+    # ---- query batch (host, pinned): reference-image + text CLIP features and target ids ---------------------
+    head = CombinerSimple(D, 4 * D, 8 * D, mode="bf16")
+    head.load_state_dict(syn.combiner_state(7, D))
+    head = head.to(dev).eval()
+    img_h = syn.features(8, Q, D).pin_memory()
+    txt_h = syn.features(9, Q, D).pin_memory()
+    tgt_h = torch.randint(0, N, (Q,), generator=torch.Generator().manual_seed(10), dtype=torch.int32).pin_memory()
+    img_d, txt_d, tgt_d = img_h.to(dev), txt_h.to(dev), tgt_h.to(dev)
+    ids_h = torch.empty((Q, K), dtype=torch.int32).pin_memory()
+    val_h = torch.empty((Q, K), dtype=torch.float32).pin_memory()
+    cnt_h = torch.empty(len(KS), dtype=torch.int32).pin_memory()
+
+    sim_ms = []
+
+    def step(img, txt, tgt, timed_sim=None):
+        with torch.no_grad():
+            _, qb = head(img, txt, want_bf16=True)                       # fusion head -> bf16 unit-norm queries
+        if timed_sim is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        vals, ids, _keys, status = sharded.sharded_topk(qb, gallery, K, begin, check_overflow=False)
+        if timed_sim is not None:
+            e1.record()
+            timed_sim.append((e0, e1))
+        counts, _ranks = ops.recall_at_k(ids, class_of, tgt, KS)
+        return vals, ids, counts, status
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, time.time()
+
+    # ---- warm-up, then `value`: inputs resident in HBM -------------------------------------------------------
+    out = step(img_d, txt_d, tgt_d)
+    # plant each query's target at a chosen rank of its own ranking so that Recall@K is non-trivial
+    planted = syn.planted_ranks(11, Q, max_rank=K).to(dev)
+    tgt_d = out[1].gather(1, planted[:, None]).squeeze(1).contiguous()
+    tgt_h.copy_(tgt_d)
+    for _ in range(max(args.warmup, 3)):
+        out = step(img_d, txt_d, tgt_d)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = ops.launch_counter.n
+    events = []
+    ms_total, t0, t1 = timed(lambda: step(img_d, txt_d, tgt_d, events), args.steps)
+    launches = ops.launch_counter.n - l0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    sim_ms = [a.elapsed_time(b) for a, b in events]
+    ms_step = ms_total / args.steps
+    value = Q / (ms_step * 1e-3)
+
+    # ---- `e2e`: host inputs, pinned H2D per step, results read back per step ---------------------------------
+    def e2e_step():
+        img = img_h.to(dev, non_blocking=True)
+        txt = txt_h.to(dev, non_blocking=True)
+        tgt = tgt_h.to(dev, non_blocking=True)
+        vals, ids, counts, _ = step(img, txt, tgt)
+        ids_h.copy_(ids, non_blocking=True)
+        val_h.copy_(vals, non_blocking=True)
+        cnt_h.copy_(counts, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                        # the caller consumes the result on the host
+
+    e2e_step()
+    ms_e2e, _, _ = timed(e2e_step, args.steps)
+    e2e_value = Q / (ms_e2e / args.steps * 1e-3)
+    h2d = img_h.numel() * 4 + txt_h.numel() * 4 + tgt_h.numel() * 4
+    d2h = ids_h.numel() * 4 + val_h.numel() * 4 + cnt_h.numel() * 4
+    status_ok = int(out[3][0].item()) == 0                               # no candidate-list overflow on this rank
+
+    # ---- roofline of the dominant kernel (sim_topk_tc_kernel, all launches of one step on this rank) ---------
+    pk = peaks()
+    flop_rank = 2.0 * Q * rows * D                                        # 2*D FLOP per (query,row)
+    sim_avg_ms = sum(sim_ms) / max(len(sim_ms), 1)
+    achieved = flop_rank / (sim_avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                "kernel": "ern::simtc::sim_topk_tc_kernel (all launches of one step incl. the interleaved "
+                          "select_topk_kernel launches, CUDA events on the launching stream)",
+                "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                "frac_of_burst_peak": achieved / pk["bf16_burst"],
+                "hbm_gbs_achieved": rows * D * 2 / (sim_avg_ms * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"]}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            _, _, cpu_baseline = cpu_reference_qps(args)
+        recall = [float(100.0 * c / Q) for c in out[2].cpu().tolist()]
+        line = {
+            "metric": "queries/sec (top-100, 640-d)", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "recall_at": dict(zip([str(k) for k in KS], recall)), "status_ok": status_ok,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,10 +44,11 @@ def sharded_topk(queries: torch.Tensor, local_gallery: torch.Tensor, k: int, id_
                  mode: int = MODE_BF16, rank_by: int = RANK_SIMILARITY, exclude_ids: Optional[torch.Tensor] = None,
                  group: Optional[dist.ProcessGroup] = None, check_overflow: bool = True):
     """Global top-k of every (replicated) query over a row-sharded gallery.
-    Returns ``(values [Q,k], global ids [Q,k], keys [Q,k])``, identical on every rank."""
-    _, _, keys, _ = ops.sim_topk(queries, local_gallery, k, mode=mode, rank_by=rank_by, exclude_ids=exclude_ids,
+    Returns ``(values [Q,k], global ids [Q,k], keys [Q,k], status int32[4])``; the first three are identical on
+    every rank, ``status`` is this rank's overflow report (see ``ops.sim_topk``)."""
+    _, _, keys, status = ops.sim_topk(queries, local_gallery, k, mode=mode, rank_by=rank_by, exclude_ids=exclude_ids,
                                  id_offset=id_offset, want_keys=True, check_overflow=check_overflow)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return ops.topk_merge(keys.unsqueeze(0), k)
+        return (*ops.topk_merge(keys.unsqueeze(0), k), status)
     gathered = exchange_candidates(keys, group)
-    return ops.topk_merge(gathered, k)
+    return (*ops.topk_merge(gathered, k), status)
