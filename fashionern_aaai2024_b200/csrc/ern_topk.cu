@@ -13,15 +13,45 @@ namespace ern {
 constexpr int kSelectThreads = 256;
 
 
+__device__ __forceinline__ void bitonic_sort_desc(uint64_t* a, int pow2, int tid) {
+  for (int size = 2; size <= pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < (pow2 >> 1); i += kSelectThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const uint64_t x = a[lo], y = a[hi];
+        const bool desc = (lo & size) == 0;
+        if ((x < y) == desc) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kSmallSort = 256;  // candidates that are sorted directly / survivors of the radix select
+
 __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const SelectParams p) {
   __shared__ uint64_t keys[ERN_SORT_CAP];
-  __shared__ int n_shared;
+  __shared__ uint64_t top[kSmallSort];
+  __shared__ int hist[256];
+  __shared__ int n_shared, m_shared, remaining_sh;
+  __shared__ uint32_t prefix_sh;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  if (tid == 0) n_shared = 0;
+  const int k = p.k;
+  if (tid == 0) {
+    n_shared = 0;
+    m_shared = 0;
+    remaining_sh = k;
+    prefix_sh = 0;
+  }
   __syncthreads();
 
-  // ---- gather the non-empty candidates densely into shared memory (order is irrelevant: they get sorted)
+  // ---- gather the non-empty candidates densely into shared memory (order is irrelevant) ----------------
   auto push = [&](uint64_t key) {
     if (key != 0ull) {
       const int pos = atomicAdd(&n_shared, 1);
@@ -39,11 +69,12 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
     } else {
       const int prev = p.prev_counts[q];
       for (int i = tid; i < prev; i += kSelectThreads) push(list[i]);
-      const int span = p.n_chunks * p.seg_size;
       int32_t* sc = p.seg_counts + q * ERN_MAX_CHUNKS;
-      for (int i = tid; i < span; i += kSelectThreads) {
-        const int c = i / p.seg_size, off = i - c * p.seg_size;
-        if (off < sc[c]) push(list[p.keep + i]);
+      // one warp per segment: coalesced reads of exactly the published entries
+      for (int c = tid >> 5; c < p.n_chunks; c += kSelectThreads / 32) {
+        const int cnt = min(sc[c], p.seg_size);
+        const uint64_t* seg = list + p.keep + c * p.seg_size;
+        for (int i = tid & 31; i < cnt; i += 32) push(seg[i]);
       }
       __syncthreads();
       if (tid < p.n_chunks) {
@@ -58,38 +89,97 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
     if (tid == 0 && p.status) atomicAdd(&p.status[0], 1);
     n = ERN_SORT_CAP;
   }
-  int pow2 = 32;
-  while (pow2 < n) pow2 <<= 1;
-  for (int i = n + tid; i < pow2; i += kSelectThreads) keys[i] = 0ull;
 
-  // ---- bitonic sort, descending
-  for (int size = 2; size <= pow2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+  const uint64_t* sorted = keys;   // array whose first min(n,k) entries are the answer, descending
+  int sorted_len = 0;
+  if (n <= kSmallSort) {
+    int pow2 = 32;
+    while (pow2 < n) pow2 <<= 1;
+    for (int i = n + tid; i < pow2; i += kSelectThreads) keys[i] = 0ull;
+    bitonic_sort_desc(keys, pow2, tid);
+    sorted_len = pow2;
+  } else {
+    // ---- radix select (4 x 8 bits, MSB first) of the k-th largest 32-bit ranking value, then sort only the
+    //      candidates that reach it.  Ties at the threshold are all kept, so the result stays exact.
+    uint32_t mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0;
       __syncthreads();
-      for (int i = tid; i < (pow2 >> 1); i += kSelectThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const uint64_t a = keys[lo], b = keys[hi];
-        const bool desc = (lo & size) == 0;
-        if ((a < b) == desc) {
-          keys[lo] = b;
-          keys[hi] = a;
+      const uint32_t prefix = prefix_sh;
+      for (int i = tid; i < n; i += kSelectThreads) {
+        const uint32_t h = static_cast<uint32_t>(keys[i] >> 32);
+        if ((h & mask) == prefix) atomicAdd(&hist[(h >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        int c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          c[j] = hist[tid * 8 + j];
+          sum += c[j];
+        }
+        // above = number of matching candidates in bins owned by higher lanes
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_down_sync(0xffffffffu, incl, o);
+          if (tid + o < 32) incl += v;
+        }
+        int above = incl - sum;
+        const int remaining = remaining_sh;
+        __syncwarp();
+        if (above < remaining && remaining <= above + sum) {
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {
+            if (above < remaining && remaining <= above + c[j]) {
+              prefix_sh = prefix | (static_cast<uint32_t>(tid * 8 + j) << shift);
+              remaining_sh = remaining - above;
+              above = 1 << 30;   // found; stop matching
+            } else if (above < (1 << 30)) {
+              above += c[j];
+            }
+          }
         }
       }
+      mask |= 0xFFu << shift;
+      __syncthreads();
+    }
+    const uint32_t thr32 = prefix_sh;
+    for (int i = tid; i < n; i += kSelectThreads) {
+      const uint64_t key = keys[i];
+      if (static_cast<uint32_t>(key >> 32) >= thr32) {
+        const int pos = atomicAdd(&m_shared, 1);
+        if (pos < kSmallSort) top[pos] = key;
+      }
+    }
+    __syncthreads();
+    const int m = m_shared;
+    if (m <= kSmallSort) {
+      int pow2 = 32;
+      while (pow2 < m) pow2 <<= 1;
+      for (int i = m + tid; i < pow2; i += kSelectThreads) top[i] = 0ull;
+      bitonic_sort_desc(top, pow2, tid);
+      sorted = top;
+      sorted_len = pow2;
+    } else {
+      // more than kSmallSort candidates tie at the threshold value: sort everything
+      int pow2 = 32;
+      while (pow2 < n) pow2 <<= 1;
+      for (int i = n + tid; i < pow2; i += kSelectThreads) keys[i] = 0ull;
+      bitonic_sort_desc(keys, pow2, tid);
+      sorted_len = pow2;
     }
   }
-  __syncthreads();
 
-  const int k = p.k;
   for (int j = tid; j < k; j += kSelectThreads) {
-    const uint64_t key = (j < pow2) ? keys[j] : 0ull;
+    const uint64_t key = (j < sorted_len) ? sorted[j] : 0ull;
     if (p.lists) p.lists[q * p.cap + j] = key;
     if (p.out_keys) p.out_keys[q * k + j] = key;
     if (p.out_scores) p.out_scores[q * k + j] = key ? key_value(key) : -INFINITY;
     if (p.out_ids) p.out_ids[q * k + j] = key ? key_id(key) : -1;
   }
   if (tid == 0) {
-    const uint64_t kth = (k - 1 < pow2) ? keys[k - 1] : 0ull;
+    const uint64_t kth = (k - 1 < sorted_len) ? sorted[k - 1] : 0ull;
     if (p.prev_counts) p.prev_counts[q] = n < k ? n : k;
     // fewer than k real candidates so far: no lower bound yet
     if (p.thresholds) p.thresholds[q] = kth ? key_value(kth) : -INFINITY;
