@@ -55,12 +55,19 @@ struct SimWorkspace {
   float* thr;
   size_t bytes;
 };
+// slots per query: small batches get longer lists so that the gallery can be cut into more (smaller) chunks
+static int list_cap(int64_t nq) { return nq <= 1024 ? 4 * ERN_LIST_CAP : ERN_LIST_CAP; }
+// every segment keeps >= 62 slots: >= 5x the expected survivors per chunk at growth 8, k <= 128
+static int chunk_limit(int cap, int keep) {
+  const int c = (cap - keep) / 62;
+  return c < 1 ? 1 : (c > ERN_MAX_CHUNKS ? ERN_MAX_CHUNKS : c);
+}
 static SimWorkspace carve_sim(void* base, int64_t nq) {
   SimWorkspace w;
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
   w.lists = reinterpret_cast<uint64_t*>(p + off);
-  off += align256(static_cast<size_t>(nq) * ERN_LIST_CAP * 8);
+  off += align256(static_cast<size_t>(nq) * list_cap(nq) * 8);
   w.prev_counts = reinterpret_cast<int32_t*>(p + off);
   off += align256(static_cast<size_t>(nq) * 4);
   w.seg_counts = reinterpret_cast<int32_t*>(p + off);
@@ -231,7 +238,7 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
   sink.thresholds = ws.thr;
   sink.exclude = exclude_id_dev;
   sink.status = status_dev;
-  sink.cap = ERN_LIST_CAP;
+  sink.cap = list_cap(nq);
   sink.keep = k;
   sink.id_offset = id_offset;
   sink.nq = nq;
@@ -239,7 +246,7 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
   SelectParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.lists = ws.lists;
-  sp.cap = ERN_LIST_CAP;
+  sp.cap = list_cap(nq);
   sp.keep = k;
   sp.prev_counts = ws.prev_counts;
   sp.seg_counts = ws.seg_counts;
@@ -266,7 +273,7 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
     sink.dense = first ? 1 : 0;
     sink.row_begin = begin;
     sink.row_end = end;
-    sink.n_chunks = (growth == 1) ? 1 : ERN_MAX_CHUNKS;   // upper bound; the launcher picks the actual split
+    sink.n_chunks = (growth == 1) ? 1 : chunk_limit(sink.cap, sink.keep);   // upper bound; the launcher picks the split
     sink.seg_size = (sink.cap - sink.keep) / sink.n_chunks;
     if (end > begin) {
       if (mode == ERN_MODE_FP32) {

@@ -365,6 +365,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, in
   int units = pair ? sm_count / 2 : sm_count;
   // on entry sink.n_chunks is the caller's upper bound on chunks (1 for the overflow-proof schedule)
   const int max_chunks = sink.n_chunks > 0 && sink.n_chunks < ERN_MAX_CHUNKS ? sink.n_chunks : ERN_MAX_CHUNKS;
+  // (the selection kernel walks segments with one warp each; ERN_MAX_CHUNKS bounds the seg_counts row)
   plan_chunks(p.n_qtiles, p.tiles_total, units, max_chunks, &p.n_chunks, &p.tiles_per_chunk);
   sink.n_chunks = p.n_chunks;
   sink.seg_size = (sink.cap - sink.keep) / p.n_chunks;

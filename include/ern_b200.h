@@ -54,12 +54,13 @@ extern "C" {
 #define ERN_RANK_REFERENCE 1  /* -(1 - s) rounded in fp32: the reference's `1 - pred @ index.T`    */
                               /* (run/test/test_fiq.py:49) with its rounding-induced ties          */
 
-/* max k of the streaming top-k; slots of one query's candidate list; max candidates one selection/merge
- * pass can take; max gallery chunks (= independent writers) per query and launch */
+/* max k of the streaming top-k; slots of one query's candidate list (x4 for batches of <= 1024 queries, which
+ * need more, smaller gallery chunks to fill the GPU); max candidates one selection/merge pass can take; max
+ * gallery chunks (= independent writers) per query and launch */
 #define ERN_MAX_K 128
 #define ERN_LIST_CAP 4096
 #define ERN_SORT_CAP 2048
-#define ERN_MAX_CHUNKS 64
+#define ERN_MAX_CHUNKS 256
 /* gallery rows scored densely (every score kept) before thresholds exist */
 #define ERN_DENSE_ROWS 256
 
