@@ -3,6 +3,7 @@
 Public surface (mirrors the reference's own, see DESIGN.md / INTEGRATION.md):
 
   CombinerSimple, accelerate_ern            fusion head            (models/fusion_model.py:58-94)
+  VisualSR                                  patch attention pooling (models/fusion_model.py:97-154; 'next' row)
   compute_{fiq,shoes,200k,cirr}_val_metrics metric tails           (run/test/test_*.py, run/valid/validate_*.py)
   compute_val_metrics, score_topk_recall
   ops.*                                     tensor-level wrappers of the C ABI (include/ern_b200.h)
@@ -12,6 +13,7 @@ All compute is hand-written CUDA behind ``libern_b200.so``; there is no CPU or t
 """
 from ._lib import ErnError, MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARITY  # noqa: F401
 from .combiner import CombinerSimple, accelerate_ern  # noqa: F401
+from .visual_sr import VisualSR  # noqa: F401
 from . import ops, sharded  # noqa: F401
 from .metrics import (compute_200k_val_metrics, compute_cirr_val_metrics, compute_fiq_val_metrics,  # noqa: F401
                       compute_shoes_val_metrics, compute_val_metrics, score_topk_recall, set_precision,

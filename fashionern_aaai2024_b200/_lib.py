@@ -27,6 +27,7 @@ SYMBOLS = (
     "ern_combiner_packed_bytes", "ern_combiner_pack", "ern_combiner_workspace_bytes", "ern_combiner_forward",
     "ern_sim_topk_workspace_bytes", "ern_sim_topk", "ern_topk_merge", "ern_recall_at_k",
     "ern_cirr_subset_recall",
+    "ern_visualsr_packed_bytes", "ern_visualsr_pack", "ern_visualsr_workspace_bytes", "ern_visualsr_forward",
 )
 
 
@@ -37,6 +38,12 @@ class ErnError(RuntimeError):
 class CombinerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w_text", "b_text", "w_image", "b_image", "w_hid", "b_hid",
                                           "w_gate", "b_gate", "packed_bf16")]
+
+
+class VisualSRWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_local", "b_local", "bn_local_scale", "bn_local_shift", "w_global",
+                                          "b_global", "bn_global_scale", "bn_global_shift", "w_common", "b_common",
+                                          "packed_bf16")]
 
 
 _lib: Optional[C.CDLL] = None
@@ -70,6 +77,12 @@ def lib() -> C.CDLL:
     l.ern_recall_at_k.argtypes = [vp, i64, i32, vp, i64, vp, C.POINTER(C.c_int32), i32, vp, vp, vp]
     l.ern_cirr_subset_recall.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, i32,
                                          C.POINTER(C.c_int32), i32, vp, vp, vp]
+    l.ern_visualsr_packed_bytes.argtypes = [i32]
+    l.ern_visualsr_packed_bytes.restype = sz
+    l.ern_visualsr_pack.argtypes = [C.POINTER(VisualSRWeights), i32, vp, vp]
+    l.ern_visualsr_workspace_bytes.argtypes = [i64, i32, i32, i32]
+    l.ern_visualsr_workspace_bytes.restype = sz
+    l.ern_visualsr_forward.argtypes = [C.POINTER(VisualSRWeights), i32, i32, i32, vp, i64, vp, vp, sz, vp]
     for name in SYMBOLS:
         fn = getattr(l, name)
         if fn.restype is C.c_int and name not in ("ern_version",):

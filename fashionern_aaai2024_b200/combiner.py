@@ -113,17 +113,22 @@ class CombinerSimple(nn.Module):
 
 def accelerate_ern(model: nn.Module, mode: str = "bf16") -> nn.Module:
     """Swap every reference ``CombinerSimple`` inside an ``ERN`` (models/model.py:16-20: ``DVR.combiner_global``,
-    ``DVR.combiner_local``, ``DVR.combiner``, ``Combiner_module``) for the B200 head, keeping its weights."""
+    ``DVR.combiner_local``, ``DVR.combiner``, ``Combiner_module``) and every reference ``VisualSR`` (``SR_module``,
+    ``DVR.SR_module``) for the B200 modules, keeping their weights and buffers."""
+    from .visual_sr import VisualSR
     for name, child in list(model.named_children()):
-        is_ref_head = (type(child).__name__ == "CombinerSimple" and not isinstance(child, CombinerSimple)
-                       and hasattr(child, "dynamic_scalar"))
-        if is_ref_head:
+        cls = type(child).__name__
+        if cls == "CombinerSimple" and not isinstance(child, CombinerSimple) and hasattr(child, "dynamic_scalar"):
             dim = child.text_projection_layer[0].in_features
             new = CombinerSimple(dim, dim * 4, dim * 8, mode=mode)
-            new.load_state_dict(child.state_dict())
-            new = new.to(next(child.parameters()).device).float()
-            new.train(child.training)
-            setattr(model, name, new)
+        elif cls == "VisualSR" and not isinstance(child, VisualSR) and hasattr(child, "embedding_common"):
+            dim = child.embedding_common.in_features
+            new = VisualSR(dim, num_region=child.embedding_local[1].num_features, mode=mode)
         else:
             accelerate_ern(child, mode)
+            continue
+        new.load_state_dict(child.state_dict())
+        new = new.to(next(child.parameters()).device).float()
+        new.train(child.training)
+        setattr(model, name, new)
     return model

@@ -179,6 +179,50 @@ int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+size_t ern_visualsr_packed_bytes(int dim) { return visualsr::packed_bytes(dim); }
+
+int ern_visualsr_pack(const ern_visualsr_weights* w, int dim, void* packed_dev, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(w && w->w_local && w->w_global && packed_dev && dim > 0, "bad arguments");
+  return visualsr::pack(w, dim, packed_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t ern_visualsr_workspace_bytes(int64_t rows, int patches, int dim, int mode) {
+  if (rows < 0 || patches <= 0 || dim <= 0) return 0;
+  return visualsr::workspace_bytes(rows, patches, dim, mode);
+}
+
+int ern_visualsr_forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const float* local_dev,
+                         int64_t rows, float* out_f32_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(w && local_dev && out_f32_dev && rows >= 0 && dim > 0, "bad arguments");
+  ERN_REQUIRE(patches >= 1 && patches <= 32, "patches must be in [1,32]");
+  ERN_REQUIRE(w->w_local && w->b_local && w->bn_local_scale && w->bn_local_shift && w->w_global && w->b_global &&
+                  w->bn_global_scale && w->bn_global_shift && w->w_common && w->b_common,
+              "all ten parameter tensors are required");
+  if (workspace_bytes < ern_visualsr_workspace_bytes(rows, patches, dim, mode) || (!workspace_dev && rows > 0)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, ern_visualsr_workspace_bytes(rows, patches, dim, mode));
+    return ERN_ERR_WORKSPACE;
+  }
+  if (mode == ERN_MODE_BF16) {
+    ERN_REQUIRE(w->packed_bf16, "bf16 mode needs packed weights (ern_visualsr_pack)");
+    if (dim % 128 != 0) {
+      set_error("bf16 VisualSR needs dim %% 128 == 0 (got %d)", dim);
+      return ERN_ERR_UNSUPPORTED;
+    }
+  } else if (mode != ERN_MODE_FP32) {
+    set_error("unknown mode %d", mode);
+    return ERN_ERR_ARG;
+  }
+  return visualsr::forward(w, dim, patches, mode, local_dev, rows, out_f32_dev, workspace_dev, di.sm_count,
+                           static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode) {
   (void)dim;
   (void)mode;

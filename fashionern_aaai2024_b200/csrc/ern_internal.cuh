@@ -49,4 +49,12 @@ int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, con
                  cudaStream_t st);
 }
 
+namespace visualsr {
+size_t packed_bytes(int dim);
+int pack(const ern_visualsr_weights* w, int dim, void* packed, cudaStream_t st);
+size_t workspace_bytes(int64_t rows, int patches, int dim, int mode);
+int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const float* local, int64_t rows,
+            float* out, void* workspace, int sm_count, cudaStream_t st);
+}
+
 }  // namespace ern

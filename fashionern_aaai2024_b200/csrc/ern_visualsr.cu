@@ -1,0 +1,224 @@
+// VisualSR.forward (models/fusion_model.py:141-154) -- SURVEY.md 8(f) "next" row 1: the attention pooling of the
+// 13 patch embeddings that feeds the gallery-side fusion head (models/model.py:65) and the DVR module
+// (models/fusion_model.py:48).  Eval mode: Dropout = identity, BatchNorm1d = per-channel affine (folded by the
+// caller into scale/shift).
+//
+//   raw_global = mean_p local[b,p,:]                                         (:142)
+//   l_emb[b,p,:] = tanh(bn_P (local[b,p,:] Wl^T + bl))                        (:145; BatchNorm1d(13): channel = p)
+//   g_emb[b,:]   = tanh(bn_D (raw_global  Wg^T + bg))                         (:146; BatchNorm1d(D): channel = d)
+//   logit[b,p]   = (l_emb[b,p,:] * g_emb[b,:]) . wc + bc ; w = softmax_p      (:149-150)
+//   out[b,:]     = sum_p w[b,p] local[b,p,:] ;  out / (||out|| + 1e-8)        (:153-154, :136-139)
+//
+// The [B*13, D] x [D, D] GEMM runs on the tensor cores (ern_gemm_tc.cuh); its epilogue applies the affine, tanh and
+// the product with c[b,:] = g_emb[b,:] * wc and row-reduces, so l_emb never reaches HBM.
+#include "ern_gemm_tc.cuh"
+
+namespace ern {
+namespace visualsr {
+
+constexpr int kMaxPatches = 32;
+
+// one warp per row b: mean over patches (+ bf16 copies of the patch matrix and of the mean for the GEMMs)
+__global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, int patches, int dim,
+                               float* __restrict__ mean_f32, __nv_bfloat16* __restrict__ mean_b,
+                               __nv_bfloat16* __restrict__ local_b) {
+  const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= rows) return;
+  const float* x = local + b * patches * dim;
+  for (int d = lane; d < dim; d += 32) {
+    float s = 0.f;
+    for (int p = 0; p < patches; ++p) {
+      const float v = x[p * dim + d];
+      s += v;
+      if (local_b) local_b[(b * patches + p) * dim + d] = __float2bfloat16_rn(v);
+    }
+    const float m = s / static_cast<float>(patches);
+    if (mean_f32) mean_f32[b * dim + d] = m;
+    if (mean_b) mean_b[b * dim + d] = __float2bfloat16_rn(m);
+  }
+}
+
+// fp32 validation GEMM, 64x64 tiles (see ern_combiner.cu for the tile structure); kLocal selects the epilogue
+constexpr int kTile = 64;
+constexpr int kKc = 16;
+constexpr int kF32Threads = 256;
+
+template <bool kLocal>
+__global__ void __launch_bounds__(kF32Threads)
+linear_tanh_f32_kernel(const float* __restrict__ X, int64_t rows, const float* __restrict__ W, int K, int N,
+                       const float* __restrict__ bias, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ wc, float* __restrict__ out,
+                       const float* __restrict__ cvec, int patches, float* __restrict__ partial, int n_tiles) {
+  __shared__ float xs[kKc][kTile + 1];
+  __shared__ float ws[kKc][kTile + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kTile;
+  const int n0 = blockIdx.x * kTile;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += kKc) {
+    for (int e = threadIdx.x; e < kTile * kKc; e += kF32Threads) {
+      const int r = e / kKc, kk = e % kKc;
+      const bool kin = (k0 + kk) < K;
+      xs[kk][r] = (kin && r0 + r < rows) ? X[(r0 + r) * K + k0 + kk] : 0.f;
+      ws[kk][r] = (kin && n0 + r < N) ? W[static_cast<int64_t>(n0 + r) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kKc; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = xs[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty * 4 + i;
+    const int64_t rr = r < rows ? r : 0;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      const float lin = acc[i][j] + bias[n];
+      if (kLocal) {
+        const int p = static_cast<int>(rr % patches);
+        dot = fmaf(tanhf(fmaf(scale[p], lin, shift[p])), cvec[(rr / patches) * N + n], dot);
+      } else if (r < rows) {
+        out[r * N + n] = tanhf(fmaf(scale[n], lin, shift[n])) * wc[n];
+      }
+    }
+    if (kLocal) {
+      for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (tx == 0 && r < rows) partial[r * n_tiles + blockIdx.x] = dot;
+    }
+  }
+}
+
+// one warp per row b: logits -> softmax over the patches -> weighted sum of the fp32 patch features -> l2norm(+1e-8)
+__global__ void finalize_kernel(const float* __restrict__ local, int64_t rows, int patches, int dim,
+                                const float* __restrict__ partial, int n_tiles, const float* __restrict__ b_common,
+                                float* __restrict__ out) {
+  const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= rows) return;
+  float logit = -INFINITY;
+  if (lane < patches) {
+    float z = 0.f;
+    for (int t = 0; t < n_tiles; ++t) z += partial[(b * patches + lane) * n_tiles + t];
+    logit = z + b_common[0];
+  }
+  float mx = logit;
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e = lane < patches ? expf(logit - mx) : 0.f;
+  float sum = e;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float w = e / sum;
+  const float* x = local + b * patches * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    float acc = 0.f;
+    for (int p = 0; p < patches; ++p) acc = fmaf(__shfl_sync(0xffffffffu, w, p), x[p * dim + d], acc);
+    out[b * dim + d] = acc;
+    ss = fmaf(acc, acc, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float denom = sqrtf(ss) + 1e-8f;
+  for (int d = lane; d < dim; d += 32) out[b * dim + d] = out[b * dim + d] / denom;
+}
+
+static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+constexpr int kTcBlockN = 128;
+
+size_t packed_bytes(int dim) { return al(static_cast<size_t>(dim) * dim * 2) * 2 + 256; }
+
+int pack(const ern_visualsr_weights* w, int dim, void* packed, cudaStream_t st) {
+  const int64_t n = static_cast<int64_t>(dim) * dim;
+  uint8_t* p = static_cast<uint8_t*>(packed);
+  int rc = combiner::launch_cast_bf16(w->w_local, p, n, st);
+  if (rc) return rc;
+  return combiner::launch_cast_bf16(w->w_global, p + al(n * 2), n, st);
+}
+
+size_t workspace_bytes(int64_t rows, int patches, int dim, int mode) {
+  const size_t r = rows, P = patches, d = dim;
+  if (mode == ERN_MODE_FP32) return al(r * d * 4) * 2 + al(r * P * cdiv(dim, kTile) * 4) + 512;
+  return al(r * P * d * 2) + al(r * d * 2) + al(r * d * 4) + al(r * P * (d / kTcBlockN) * 4) + 512;
+}
+
+int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const float* local, int64_t rows,
+            float* out, void* workspace, int sm_count, cudaStream_t st) {
+  if (rows <= 0) return ERN_OK;
+  const size_t r = rows, P = patches, d = dim;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const int warp_blocks = cdiv(rows * 32, 256);
+  if (mode == ERN_MODE_FP32) {
+    float* mean = reinterpret_cast<float*>(ws);
+    float* cvec = reinterpret_cast<float*>(ws + al(r * d * 4));
+    float* partial = reinterpret_cast<float*>(ws + 2 * al(r * d * 4));
+    const int n_tiles = cdiv(dim, kTile);
+    prepare_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, mean, nullptr, nullptr);
+    ERN_REQUIRE(cdiv(rows * patches, kTile) <= 65535, "too many rows for one fp32 VisualSR call; split the batch");
+    linear_tanh_f32_kernel<false><<<dim3(n_tiles, cdiv(rows, kTile)), kF32Threads, 0, st>>>(
+        mean, rows, w->w_global, dim, dim, w->b_global, w->bn_global_scale, w->bn_global_shift, w->w_common, cvec,
+        nullptr, patches, nullptr, 0);
+    linear_tanh_f32_kernel<true><<<dim3(n_tiles, cdiv(rows * patches, kTile)), kF32Threads, 0, st>>>(
+        local, rows * patches, w->w_local, dim, dim, w->b_local, w->bn_local_scale, w->bn_local_shift, nullptr,
+        nullptr, cvec, patches, partial, n_tiles);
+    finalize_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, partial, n_tiles, w->b_common, out);
+    ERN_CUDA(cudaGetLastError());
+    return ERN_OK;
+  }
+  // ---- tensor-core path
+  __nv_bfloat16* local_b = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* mean_b = reinterpret_cast<__nv_bfloat16*>(ws + al(r * P * d * 2));
+  float* cvec = reinterpret_cast<float*>(ws + al(r * P * d * 2) + al(r * d * 2));
+  float* partial = reinterpret_cast<float*>(ws + al(r * P * d * 2) + al(r * d * 2) + al(r * d * 4));
+  const int n_tiles = dim / kTcBlockN;
+  const uint8_t* pk = static_cast<const uint8_t*>(w->packed_bf16);
+  const void* wl_b = pk;
+  const void* wg_b = pk + al(d * d * 2);
+  prepare_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, nullptr, mean_b, local_b);
+  ERN_CUDA(cudaGetLastError());
+  CUtensorMap t_local, t_mean, t_wl, t_wg;
+  int rc;
+  if ((rc = simtc::make_tmap_bf16_rows(&t_local, local_b, rows * patches, dim, dim))) return rc;
+  if ((rc = simtc::make_tmap_bf16_rows(&t_mean, mean_b, rows, dim, dim))) return rc;
+  if ((rc = simtc::make_tmap_bf16_rows(&t_wl, wl_b, dim, dim, dim))) return rc;
+  if ((rc = simtc::make_tmap_bf16_rows(&t_wg, wg_b, dim, dim, dim))) return rc;
+  gemmtc::Params g{};
+  g.m = rows;
+  g.n = dim;
+  g.k = dim;
+  g.bias = w->b_global;
+  g.wg = w->w_common;
+  g.scale = w->bn_global_scale;
+  g.shift = w->bn_global_shift;
+  g.out_f32 = cvec;
+  g.ldo = dim;
+  if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrGlobal>(t_mean, t_wg, g, sm_count, st))) return rc;
+  gemmtc::Params l{};
+  l.m = rows * patches;
+  l.n = dim;
+  l.k = dim;
+  l.bias = w->b_local;
+  l.scale = w->bn_local_scale;
+  l.shift = w->bn_local_shift;
+  l.cvec = cvec;
+  l.patches = patches;
+  l.partial = partial;
+  if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrLocal>(t_local, t_wl, l, sm_count, st))) return rc;
+  finalize_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, partial, n_tiles, w->b_common, out);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+}  // namespace visualsr
+}  // namespace ern

@@ -48,6 +48,35 @@ def combiner_state(seed: int, dim: int, scale: float = 1.0) -> Dict[str, torch.T
     return sd
 
 
+def visualsr_state(seed: int, dim: int, patches: int = PATCHES) -> Dict[str, torch.Tensor]:
+    """State dict of one ``VisualSR(dim)`` with the reference's key names (models/fusion_model.py:106-124):
+    Xavier-uniform Linear weights like its ``init_weights`` (:126-134) but non-trivial biases and BatchNorm
+    affine/running statistics, so that every term of the eval-mode forward is exercised."""
+    g = _gen(seed)
+
+    def xavier(out_f, in_f):
+        r = float(np.sqrt(6.0) / np.sqrt(in_f + out_f))
+        return (torch.rand(out_f, in_f, generator=g) * 2 - 1) * r
+
+    def bn(prefix, n, sd):
+        sd[f"{prefix}.weight"] = 0.5 + torch.rand(n, generator=g)
+        sd[f"{prefix}.bias"] = 0.2 * torch.randn(n, generator=g)
+        sd[f"{prefix}.running_mean"] = 0.1 * torch.randn(n, generator=g)
+        sd[f"{prefix}.running_var"] = 0.5 + torch.rand(n, generator=g)
+        sd[f"{prefix}.num_batches_tracked"] = torch.tensor(100)
+
+    sd: Dict[str, torch.Tensor] = {}
+    sd["embedding_local.0.weight"] = xavier(dim, dim)
+    sd["embedding_local.0.bias"] = 0.05 * torch.randn(dim, generator=g)
+    bn("embedding_local.1", patches, sd)
+    sd["embedding_global.0.weight"] = xavier(dim, dim)
+    sd["embedding_global.0.bias"] = 0.05 * torch.randn(dim, generator=g)
+    bn("embedding_global.1", dim, sd)
+    sd["embedding_common.weight"] = xavier(1, dim) * 4.0
+    sd["embedding_common.bias"] = 0.1 * torch.randn(1, generator=g)
+    return sd
+
+
 def features(seed: int, rows: int, dim: int, unit: bool = False) -> torch.Tensor:
     x = torch.randn(rows, dim, generator=_gen(seed))
     if unit:

@@ -108,6 +108,34 @@ ERN_API int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mod
                          size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * VisualSR.forward in eval mode (models/fusion_model.py:141-154): attention pooling of
+ * the P (= 13) patch embeddings [rows, P, D] -> unit-norm [rows, D] (own l2norm with +1e-8, :136-139).
+ * The eval-mode BatchNorm1d layers arrive folded: scale = gamma / sqrt(running_var + eps),
+ * shift = beta - running_mean * scale (embedding_local.1 has P channels, embedding_global.1 has D).
+ * ERN_MODE_BF16 needs dim % 128 == 0 and packed weights (ern_visualsr_pack).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ern_visualsr_weights {
+  const float* w_local;         /* embedding_local.0.weight  [D, D] */
+  const float* b_local;         /* embedding_local.0.bias    [D]    */
+  const float* bn_local_scale;  /* folded embedding_local.1  [P]    */
+  const float* bn_local_shift;  /*                           [P]    */
+  const float* w_global;        /* embedding_global.0.weight [D, D] */
+  const float* b_global;        /* embedding_global.0.bias   [D]    */
+  const float* bn_global_scale; /* folded embedding_global.1 [D]    */
+  const float* bn_global_shift; /*                           [D]    */
+  const float* w_common;        /* embedding_common.weight   [1, D] */
+  const float* b_common;        /* embedding_common.bias     [1]    */
+  const void* packed_bf16;
+} ern_visualsr_weights;
+
+ERN_API size_t ern_visualsr_packed_bytes(int dim);
+ERN_API int ern_visualsr_pack(const ern_visualsr_weights* w, int dim, void* packed_dev, void* stream);
+ERN_API size_t ern_visualsr_workspace_bytes(int64_t rows, int patches, int dim, int mode);
+ERN_API int ern_visualsr_forward(const ern_visualsr_weights* w, int dim, int patches, int mode,
+                         const float* local_dev, int64_t rows, float* out_f32_dev, void* workspace_dev,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Similarity + streaming per-query top-k over one gallery shard.
  * Replaces `distances = 1 - predicted_features @ index_features.T;
  *           sorted_indices = torch.argsort(distances, dim=-1)` (run/test/test_fiq.py:49-50 and twins)

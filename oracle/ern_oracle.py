@@ -47,6 +47,28 @@ def combiner_forward(sd: Dict[str, torch.Tensor], image_features: torch.Tensor,
     return (out, s) if return_gate else out
 
 
+def visual_sr_forward(sd: Dict[str, torch.Tensor], local_feature: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """``VisualSR.forward`` in eval mode -- models/fusion_model.py:141-154 (layers :106-124, l2norm :136-139).
+    BatchNorm1d(13) sees [B,13,D]: channel = patch index; BatchNorm1d(D) sees [B,D]: channel = feature."""
+    x = local_feature.float()
+    raw_global = x.mean(dim=1)                                                                   # :142
+
+    def bn(v, prefix, shape):
+        m, var = sd[f"{prefix}.running_mean"].view(shape), sd[f"{prefix}.running_var"].view(shape)
+        return (v - m) / torch.sqrt(var + eps) * sd[f"{prefix}.weight"].view(shape) + sd[f"{prefix}.bias"].view(shape)
+
+    l_emb = torch.tanh(bn(F.linear(x, sd["embedding_local.0.weight"], sd["embedding_local.0.bias"]),
+                          "embedding_local.1", (1, -1, 1)))                                      # :145
+    g_emb = torch.tanh(bn(F.linear(raw_global, sd["embedding_global.0.weight"], sd["embedding_global.0.bias"]),
+                          "embedding_global.1", (1, -1)))                                        # :146
+    common = l_emb * g_emb.unsqueeze(1)                                                          # :149
+    logits = F.linear(common, sd["embedding_common.weight"], sd["embedding_common.bias"]).squeeze(2)
+    weights = torch.softmax(logits, dim=1)                                                       # :150
+    new_global = (weights.unsqueeze(2) * x).sum(dim=1)                                           # :153
+    norm = torch.sqrt((new_global ** 2).sum(dim=-1, keepdim=True)) + 1e-8                        # :136-139
+    return new_global / norm
+
+
 def gallery_normalize(index_features: torch.Tensor) -> torch.Tensor:
     """``F.normalize(index_features, dim=-1).float()`` -- run/test/test_fiq.py:45 (and twins)."""
     return F.normalize(index_features, dim=-1).float()

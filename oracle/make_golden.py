@@ -215,17 +215,46 @@ def make_combiner_golden(dim, rows, seed):
     return {"dim": dim, "rows": rows, "seed": seed}
 
 
+def make_visualsr_golden(dim, rows, seed):
+    ref.install()
+    from models.fusion_model import VisualSR
+    sd = syn.visualsr_state(seed, dim)
+    m = VisualSR(embed_dim=dim)
+    m.load_state_dict(sd)
+    m = m.eval().float()
+    x = syn.patch_features(seed + 1, rows, dim)
+    with torch.no_grad():
+        out = m(x)
+    mine = orc.visual_sr_forward(sd, x)
+    assert torch.allclose(mine, out, atol=2e-7, rtol=0), float((mine - out).abs().max())
+    np.savez(os.path.join(GOLDEN, f"visualsr{dim}.npz"), out=out.numpy(),
+             meta=np.array(json.dumps({"dim": dim, "rows": rows, "seed": seed,
+                                       "max_abs_diff_restatement": float((mine - out).abs().max())})))
+    return {"dim": dim, "rows": rows, "seed": seed}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-full", action="store_true")
     ap.add_argument("--only-full", action="store_true", help="keep the committed fixtures, redo the full-size pins")
+    ap.add_argument("--only-visualsr", action="store_true", help="only (re)make the VisualSR fixtures")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     report = {"torch": torch.__version__, "numpy": np.__version__, "cases": {}, "full": {}}
+    report["visualsr"] = [make_visualsr_golden(640, 40, 300), make_visualsr_golden(512, 40, 400)]
+    if args.only_visualsr:
+        with open(os.path.join(GOLDEN, "pin_report.json")) as f:
+            old = json.load(f)
+        old["visualsr"] = report["visualsr"]
+        with open(os.path.join(GOLDEN, "pin_report.json"), "w") as f:
+            json.dump(old, f, indent=1)
+        return
     if args.only_full:
         with open(os.path.join(GOLDEN, "pin_report.json")) as f:
-            report = json.load(f)
+            old = json.load(f)
+        old["visualsr"] = report["visualsr"]
+        report = old
         report["full"] = {}
     else:
         report["combiner"] = [make_combiner_golden(640, 48, 100), make_combiner_golden(512, 48, 200)]

@@ -76,3 +76,20 @@ def test_state_dict_keys_match_reference():
     sd = CombinerSimple(64, 256, 512).state_dict()
     assert sd["dynamic_scalar.0.weight"].shape == (512, 512) and sd["dynamic_scalar.3.weight"].shape == (1, 512)
     assert sd["text_projection_layer.0.weight"].shape == (256, 64)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout (authoring container)")
+def test_accelerate_ern_swaps_reference_modules_and_keeps_weights():
+    from oracle import ref_harness as ref
+    from fashionern_aaai2024_b200 import VisualSR, accelerate_ern, synthetic as syn
+    states = {n: syn.combiner_state(20 + i, 64) for i, n in enumerate(
+        ("DVR.combiner_global", "DVR.combiner_local", "DVR.combiner", "Combiner_module"))}
+    model = ref.build_ern(64, states)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    model = accelerate_ern(model, mode="fp32")
+    assert isinstance(model.Combiner_module, CombinerSimple) and isinstance(model.DVR.combiner, CombinerSimple)
+    assert isinstance(model.SR_module, VisualSR) and isinstance(model.DVR.SR_module, VisualSR)
+    after = model.state_dict()
+    assert set(after.keys()) == set(before.keys())             # checkpoints stay loadable both ways
+    assert all(torch.equal(after[k], before[k]) for k in before)
+    assert not model.Combiner_module.training                   # eval flag preserved

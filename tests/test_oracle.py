@@ -91,3 +91,14 @@ def test_compare_topk_tolerance():
     bad[0, 0], bad[0, 9] = bad[0, 9], bad[0, 0]
     with pytest.raises(AssertionError):
         orc.compare_topk(bad, None, p, g, 10, tol=1e-6)
+
+
+@pytest.mark.parametrize("dim", [640, 512])
+def test_visualsr_restatement_matches_reference(dim):
+    z, meta = load_golden(f"visualsr{dim}")
+    sd = syn.visualsr_state(meta["seed"], dim)
+    x = syn.patch_features(meta["seed"] + 1, meta["rows"], dim)
+    out = orc.visual_sr_forward(sd, x)
+    assert torch.allclose(out, torch.from_numpy(z["out"]), atol=2e-7, rtol=0)
+    n = out.norm(dim=-1)
+    assert torch.allclose(n, torch.ones_like(n), atol=1e-5)
