@@ -289,7 +289,10 @@ def main():
     sim_avg_ms = sum(sim_ms) / max(len(sim_ms), 1)
     achieved = flop_rank / (sim_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                "frac": achieved / pk["bf16_sustained"],
+                # dram__bytes_read+write of ONE profiled launch of this kernel (ncu --set full, rows [1M, 8.4M) of a
+                # 10M-row gallery, profiles/r01_sim_topk_tc_10m_ncu_full_raw.csv) next to its algorithmic bytes
+                "traffic": 11.334e9, "traffic_algorithmic": 9.395e9,
                 "kernel": "ern::simtc::sim_topk_tc_kernel (all launches of one step incl. the interleaved "
                           "select_topk_kernel launches, CUDA events on the launching stream)",
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
