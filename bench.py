@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-sample-queries", type=int, default=128)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU candidate exchange: fused peer-memory stores (p2p) or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -157,7 +159,8 @@ def workload_config(args, world):
     return {"workload": f"synthetic gallery {args.gallery_rows} rows x {args.dim}-d bf16 (unit-norm, seeded on device), "
                         f"{args.queries}-query batches, top-{args.k}, Recall@{list(KS)}",
             "gallery_rows": args.gallery_rows, "queries_per_step": args.queries, "dim": args.dim, "k": args.k,
-            "parallelism": f"gallery row-sharded over {world} GPU(s), queries replicated",
+            "parallelism": f"gallery row-sharded over {world} GPU(s), queries replicated"
+                           + (f", candidate exchange: {args.exchange}" if world > 1 else ""),
             "l2": "gallery shard >> 126 MB L2, streamed from HBM every step (no flush needed)"}
 
 
@@ -215,7 +218,7 @@ def main():
         if timed_sim is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        vals, ids, _keys, status = sharded.sharded_topk(qb, gallery, K, begin, check_overflow=False)
+        vals, ids, _keys, status = sharded.sharded_topk(qb, gallery, K, begin, check_overflow=False, exchange=args.exchange)
         if timed_sim is not None:
             e1.record()
             timed_sim.append((e0, e1))

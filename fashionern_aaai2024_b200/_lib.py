@@ -25,7 +25,7 @@ MAX_K, LIST_CAP, SORT_CAP, MAX_CHUNKS, DENSE_ROWS = 128, 4096, 2048, 256, 256
 SYMBOLS = (
     "ern_version", "ern_last_error", "ern_device_check", "ern_l2norm_rows",
     "ern_combiner_packed_bytes", "ern_combiner_pack", "ern_combiner_workspace_bytes", "ern_combiner_forward",
-    "ern_sim_topk_workspace_bytes", "ern_sim_topk", "ern_topk_merge", "ern_recall_at_k",
+    "ern_sim_topk_workspace_bytes", "ern_sim_topk", "ern_sim_topk_exchange", "ern_topk_merge", "ern_recall_at_k",
     "ern_cirr_subset_recall",
     "ern_visualsr_packed_bytes", "ern_visualsr_pack", "ern_visualsr_workspace_bytes", "ern_visualsr_forward",
 )
@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
     l.ern_sim_topk_workspace_bytes.restype = sz
     l.ern_sim_topk.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i64, vp, i32, i32, i32, i32,
                                vp, vp, vp, vp, vp, sz, vp]
+    l.ern_sim_topk_exchange.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i64, vp, i32, i32, i32, i32,
+                                        vp, i32, i32, vp, vp, sz, vp]
     l.ern_topk_merge.argtypes = [vp, i64, i32, i32, i64, i64, i32, vp, vp, vp, vp]
     l.ern_recall_at_k.argtypes = [vp, i64, i32, vp, i64, vp, C.POINTER(C.c_int32), i32, vp, vp, vp]
     l.ern_cirr_subset_recall.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, i32,

@@ -230,10 +230,11 @@ size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode) {
   return carve_sim(nullptr, nq).bytes + 256;
 }
 
-int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
-                 int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* exclude_id_dev, int k, int mode,
-                 int rank_by, int growth, float* out_scores_dev, int32_t* out_ids_dev, uint64_t* out_keys_dev,
-                 int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
+                         int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* exclude_id_dev, int k,
+                         int mode, int rank_by, int growth, float* out_scores_dev, int32_t* out_ids_dev,
+                         uint64_t* out_keys_dev, uint64_t* const* peer_keys_dev, int world, int rank,
+                         int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   DeviceInfo di;
   int rc = current_device(&di);
   if (rc) return rc;
@@ -243,7 +244,8 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
   ERN_REQUIRE(rank_by == ERN_RANK_SIMILARITY || rank_by == ERN_RANK_REFERENCE, "bad rank_by %d", rank_by);
   ERN_REQUIRE(growth >= 1 && growth <= 64, "growth must be in [1,64]");
   ERN_REQUIRE(status_dev != nullptr, "status_dev is required");
-  ERN_REQUIRE(out_scores_dev || out_ids_dev || out_keys_dev, "no output requested");
+  ERN_REQUIRE(out_scores_dev || out_ids_dev || out_keys_dev || peer_keys_dev, "no output requested");
+  ERN_REQUIRE(!peer_keys_dev || (world >= 1 && rank >= 0 && rank < world), "bad world/rank for the fused exchange");
   ERN_REQUIRE(id_offset >= 0 && id_offset + n_rows <= 0x7FFFFFFFll, "global ids must fit int32");
   ERN_REQUIRE((mode == ERN_MODE_FP32 && dtype == ERN_DTYPE_F32) || (mode == ERN_MODE_BF16 && dtype == ERN_DTYPE_BF16),
               "mode/dtype mismatch: FP32 mode takes f32 features, BF16 mode takes bf16 features");
@@ -326,7 +328,7 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
         rc = simf32::launch(static_cast<const float*>(queries_dev), ldq, static_cast<const float*>(gallery_dev), ldg,
                             dim, sink, rank_by, st);
       } else {
-        rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, st);
+        rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, gallery_dev, n_rows, ldg, st);
       }
       if (rc) return rc;
     }
@@ -337,12 +339,35 @@ int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* g
     sp.out_scores = last ? out_scores_dev : nullptr;
     sp.out_ids = last ? out_ids_dev : nullptr;
     sp.out_keys = last ? out_keys_dev : nullptr;
+    sp.peer_keys = last ? peer_keys_dev : nullptr;
+    sp.world = world;
+    sp.rank = rank;
+    sp.nq_total = nq;
     rc = launch_select(sp, nq, st);
     if (rc) return rc;
     begin = end;
     first = false;
   } while (begin < n_rows);
   return ERN_OK;
+}
+
+int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
+                 int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* exclude_id_dev, int k, int mode,
+                 int rank_by, int growth, float* out_scores_dev, int32_t* out_ids_dev, uint64_t* out_keys_dev,
+                 int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return sim_topk_impl(queries_dev, nq, ldq, gallery_dev, n_rows, ldg, dim, dtype, id_offset, exclude_id_dev, k, mode,
+                       rank_by, growth, out_scores_dev, out_ids_dev, out_keys_dev, nullptr, 0, 0, status_dev,
+                       workspace_dev, workspace_bytes, stream);
+}
+
+int ern_sim_topk_exchange(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
+                          int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* exclude_id_dev, int k,
+                          int mode, int rank_by, int growth, uint64_t* const* peer_keys_dev, int world, int rank,
+                          int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  ERN_REQUIRE(peer_keys_dev != nullptr, "peer_keys_dev is required");
+  return sim_topk_impl(queries_dev, nq, ldq, gallery_dev, n_rows, ldg, dim, dtype, id_offset, exclude_id_dev, k, mode,
+                       rank_by, growth, nullptr, nullptr, nullptr, peer_keys_dev, world, rank, status_dev,
+                       workspace_dev, workspace_bytes, stream);
 }
 
 int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, int64_t list_stride,

@@ -26,7 +26,7 @@ int launch(const float* Q, int64_t ldq, const float* G, int64_t ldg, int dim, co
 namespace simtc {
 int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int dim, int64_t ld_elems);
 int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, int dim, int rank_by,
-           int force_single, int sm_count, cudaStream_t st);
+           int force_single, int sm_count, const void* gallery, int64_t gallery_rows, int64_t ldg, cudaStream_t st);
 }
 namespace combiner {
 // views into the buffer filled by ern_combiner_pack: bf16 K-major weight matrices + fp32 vectors

@@ -24,6 +24,12 @@ struct SelectParams {
   float* out_scores;         // [nq, k]
   int32_t* out_ids;          // [nq, k]
   uint64_t* out_keys;        // [nq, k]
+  // ---- fused candidate exchange (nullable): peer_keys[s] is rank s's gathered buffer [world, nq, k]; this rank's
+  //      final keys are stored straight into slot `rank` of every peer's buffer over NVLink (P2P stores)
+  uint64_t* const* peer_keys;
+  int world;
+  int rank;
+  int64_t nq_total;
   int32_t* status;
 };
 }  // namespace ern

@@ -36,6 +36,10 @@ struct Params {
   int tiles_total;      // gallery tiles of TILE_G rows in [row_begin, row_end)
   int tiles_per_chunk;
   int n_chunks;
+  const uint8_t* gallery_base;  // non-null iff gallery rows are contiguous (ld == dim): enables the L2 prefetch
+  int64_t gallery_rows;
+  int row_bytes;
+  int prefetch_tiles;   // how many gallery tiles ahead of the TMA loads the L2 prefetch runs (0 = off)
   int debug;            // profiling aid (ERN_DEBUG_FLAGS): 1 = never take the append path, 2 = skip the TMEM reads
 };
 
@@ -117,6 +121,16 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
         for (int t = t0; t < t1; ++t) {
           const int g_row = static_cast<int>(p.sink.row_begin) + t * kTileG + rank * kBlockG;
+          // The query tiles of one chunk stream the same gallery tiles in lock-step, so whoever asks first waits
+          // for HBM and everybody else waits with it.  One unit per tile (rotating) pulls the tile into L2 a few
+          // tiles ahead, so the TMA loads of all of them find it there.
+          if (p.prefetch_tiles > 0 && leader && ((t + p.prefetch_tiles) % p.n_qtiles) == qt && t + p.prefetch_tiles < t1) {
+            const int64_t prow = p.sink.row_begin + static_cast<int64_t>(t + p.prefetch_tiles) * kTileG;
+            int64_t nrows = p.gallery_rows - prow;
+            if (nrows > kTileG) nrows = kTileG;
+            if (nrows > 0)
+              ptx::prefetch_l2_bulk(p.gallery_base + prow * p.row_bytes, static_cast<uint32_t>(nrows * p.row_bytes));
+          }
           for (int kb = 0; kb < p.num_kblocks; ++kb) {
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, status, 2);
             const uint32_t full = ptx::smem_u32(&bars->full[stage]);
@@ -351,13 +365,19 @@ static void plan_chunks(int n_qtiles, int tiles_total, int units, int max_chunks
 
 // One launch of the tensor-core scoring kernel over shard rows [sink.row_begin, sink.row_end).
 int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, int dim, int rank_by,
-           int force_single, int sm_count, cudaStream_t st) {
+           int force_single, int sm_count, const void* gallery, int64_t gallery_rows, int64_t ldg, cudaStream_t st) {
   const bool pair = !force_single && sink.nq > kBlockQ;
   const int tile_g = pair ? 256 : 128;
   Params p;
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("ERN_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
+  static int pf = -1;
+  if (pf < 0) { const char* e = getenv("ERN_PREFETCH_TILES"); pf = e ? atoi(e) : 4; }
+  p.gallery_base = (ldg == dim) ? static_cast<const uint8_t*>(gallery) : nullptr;
+  p.gallery_rows = gallery_rows;
+  p.row_bytes = dim * 2;
+  p.prefetch_tiles = p.gallery_base ? pf : 0;
   p.num_kblocks = dim / kBlockK;
   p.n_qtiles = cdiv(sink.nq, pair ? 2 * kBlockQ : kBlockQ);
   p.tiles_total = cdiv(sink.row_end - sink.row_begin, tile_g);

@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
     const uint64_t key = (j < sorted_len) ? sorted[j] : 0ull;
     if (p.lists) p.lists[q * p.cap + j] = key;
     if (p.out_keys) p.out_keys[q * k + j] = key;
+    if (p.peer_keys) {
+      const int64_t slot = (static_cast<int64_t>(p.rank) * p.nq_total + q) * k + j;
+      for (int s = 0; s < p.world; ++s) p.peer_keys[s][slot] = key;
+    }
     if (p.out_scores) p.out_scores[q * k + j] = key ? key_value(key) : -INFINITY;
     if (p.out_ids) p.out_ids[q * k + j] = key ? key_id(key) : -1;
   }

@@ -14,7 +14,7 @@ from . import _lib as L
 from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MAX_K, MODE_BF16, MODE_FP32, RANK_REFERENCE,
                    RANK_SIMILARITY, SORT_CAP, ErnError)
 
-__all__ = ["l2norm_rows", "sim_topk", "topk_merge", "recall_at_k", "cirr_subset_recall", "launch_counter"]
+__all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "launch_counter"]
 
 
 class _LaunchCounter:
@@ -120,6 +120,34 @@ def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int 
             if int(status[0].item()) != 0:
                 raise ErnError("candidate list overflow even with the conservative schedule (internal error)")
     return vals, ids, keys, status
+
+
+def sim_topk_exchange(queries: torch.Tensor, gallery: torch.Tensor, k: int, peer_ptrs_dev: int, world: int, rank: int,
+                      *, mode: int = MODE_BF16, rank_by: int = RANK_SIMILARITY,
+                      exclude_ids: Optional[torch.Tensor] = None, id_offset: int = 0, growth: int = 8) -> torch.Tensor:
+    """``sim_topk`` whose last launch writes this rank's [Q,k] candidate keys directly into slot ``rank`` of every
+    rank's gathered buffer through peer pointers (``peer_ptrs_dev``: device address of an array of ``world``
+    buffer pointers, e.g. ``torch.distributed._symmetric_memory`` ``buffer_ptrs_dev``).  Returns ``status``."""
+    q = _rowmajor(queries, "queries")
+    g = _rowmajor(gallery, "gallery")
+    want = torch.float32 if mode == MODE_FP32 else torch.bfloat16
+    if q.dtype != want or g.dtype != want:
+        raise ErnError(f"mode {mode} takes {want} features")
+    nq, dim = q.shape
+    dev = q.device
+    status = torch.empty(4, dtype=torch.int32, device=dev)
+    if exclude_ids is not None:
+        exclude_ids = exclude_ids.to(torch.int32).contiguous()
+    lib = L.lib()
+    with torch.cuda.device(dev):
+        wsb = lib.ern_sim_topk_workspace_bytes(nq, dim, mode)
+        ws = _workspace(wsb, dev)
+        L.check(lib.ern_sim_topk_exchange(q.data_ptr(), nq, q.stride(0), g.data_ptr(), g.shape[0], g.stride(0), dim,
+                                          DTYPE_F32 if mode == MODE_FP32 else DTYPE_BF16, int(id_offset),
+                                          L.ptr(exclude_ids), int(k), mode, rank_by, growth, peer_ptrs_dev, world,
+                                          rank, status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev)))
+        launch_counter.add(1 + 2 * _phase_count(g.shape[0], k, growth))
+    return status
 
 
 def topk_merge(keys: torch.Tensor, k_out: int):

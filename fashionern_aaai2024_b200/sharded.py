@@ -6,8 +6,11 @@ One process per GPU.  Gallery rows are block-partitioned (rank r owns rows
 Per query batch every rank
 
   1. runs the streaming top-k over ITS rows                       (ops.sim_topk, ids already global)
-  2. all-gathers the [Q,k] uint64 candidate keys over NCCL/NVLink  (8 B per candidate; 3.3 MB per rank at
-     Q=4096, k=100 -- latency-, not bandwidth-bound on NVSwitch)
+  2. exchanges the [Q,k] uint64 candidate keys (8 B per candidate; 3.3 MB per rank at Q=4096, k=100):
+       exchange="p2p"  (default when symmetric memory is available): FUSED into the last selection launch --
+                       the kernel that produces the keys stores them straight into every peer's gathered buffer
+                       over NVLink (peer pointers into torch symmetric memory), then one device-side barrier;
+       exchange="nccl" : ``all_gather_into_tensor`` of the locally written keys (also the gloo path in CPU tests)
   3. k-way merges the S sorted lists on the device                 (ops.topk_merge; ties -> lower global id)
 
 so every rank ends with the identical global top-k.  There is no other data-path collective.
@@ -40,15 +43,54 @@ def exchange_candidates(keys: torch.Tensor, group: Optional[dist.ProcessGroup] =
     return out.view((world, q) + tuple(keys.shape[1:]))
 
 
+class _PeerBuffers:
+    """Two symmetric-memory gathered buffers [S, Q, k] (double buffered so that a fast rank can start the next
+    batch's stores while a slow rank still merges the previous one) + their peer-pointer tables."""
+
+    def __init__(self, nq: int, k: int, device, group):
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size(group)
+        self.bufs, self.handles = [], []
+        gname = (group or dist.group.WORLD).group_name
+        for _ in range(2):
+            t = symm.empty((self.world, nq, k), dtype=torch.int64, device=device)
+            self.handles.append(symm.rendezvous(t, gname))
+            self.bufs.append(t)
+        self.turn = 0
+
+
+_peer_cache = {}
+
+
+def _peer_buffers(nq, k, device, group) -> _PeerBuffers:
+    key = (nq, k, device.index, id(group))
+    if key not in _peer_cache:
+        _peer_cache[key] = _PeerBuffers(nq, k, device, group)
+    return _peer_cache[key]
+
+
 def sharded_topk(queries: torch.Tensor, local_gallery: torch.Tensor, k: int, id_offset: int, *,
                  mode: int = MODE_BF16, rank_by: int = RANK_SIMILARITY, exclude_ids: Optional[torch.Tensor] = None,
-                 group: Optional[dist.ProcessGroup] = None, check_overflow: bool = True):
+                 group: Optional[dist.ProcessGroup] = None, check_overflow: bool = True, exchange: str = "nccl"):
     """Global top-k of every (replicated) query over a row-sharded gallery.
     Returns ``(values [Q,k], global ids [Q,k], keys [Q,k], status int32[4])``; the first three are identical on
     every rank, ``status`` is this rank's overflow report (see ``ops.sim_topk``)."""
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi and exchange == "p2p":
+        pb = _peer_buffers(queries.shape[0], k, queries.device, group)
+        buf, hdl = pb.bufs[pb.turn], pb.handles[pb.turn]
+        pb.turn ^= 1
+        status = ops.sim_topk_exchange(queries, local_gallery, k, hdl.buffer_ptrs_dev, pb.world, hdl.rank, mode=mode,
+                                       rank_by=rank_by, exclude_ids=exclude_ids, id_offset=id_offset)
+        if check_overflow and int(status[0].item()) != 0:          # pathological ordering: exact fallback
+            status = ops.sim_topk_exchange(queries, local_gallery, k, hdl.buffer_ptrs_dev, pb.world, hdl.rank,
+                                           mode=mode, rank_by=rank_by, exclude_ids=exclude_ids, id_offset=id_offset,
+                                           growth=1)
+        hdl.barrier(channel=0)                                      # every rank's stores have landed everywhere
+        return (*ops.topk_merge(buf, k), status)
     _, _, keys, status = ops.sim_topk(queries, local_gallery, k, mode=mode, rank_by=rank_by, exclude_ids=exclude_ids,
                                  id_offset=id_offset, want_keys=True, check_overflow=check_overflow)
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    if not multi:
         return (*ops.topk_merge(keys.unsqueeze(0), k), status)
     gathered = exchange_candidates(keys, group)
     return (*ops.topk_merge(gathered, k), status)

@@ -164,6 +164,19 @@ ERN_API int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const
                  int32_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ern_sim_topk fused with the multi-GPU candidate exchange: the last selection launch stores this
+ * rank's [nq,k] keys straight into slot `rank` of EVERY rank's gathered buffer [world, nq, k] through
+ * peer pointers (NVLink P2P stores into symmetric memory) instead of writing them locally for a
+ * separate all-gather.  peer_keys_dev: device array of `world` pointers (e.g. torch symmetric
+ * memory's buffer_ptrs_dev).  The caller inserts a cross-rank barrier before ern_topk_merge.
+ * ------------------------------------------------------------------------------------------- */
+ERN_API int ern_sim_topk_exchange(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
+                          int64_t n_rows, int64_t ldg, int dim, int dtype, int64_t id_offset,
+                          const int32_t* exclude_id_dev, int k, int mode, int rank_by, int growth,
+                          uint64_t* const* peer_keys_dev, int world, int rank, int32_t* status_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * k-way merge of per-shard / per-rank candidate lists (after the NCCL all-gather of keys):
  * list l of query q starts at keys_dev + l*list_stride + q*query_stride and holds k_in keys.
  * n_lists * k_in <= ERN_SORT_CAP.
