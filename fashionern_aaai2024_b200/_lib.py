@@ -26,7 +26,7 @@ SYMBOLS = (
     "ern_version", "ern_last_error", "ern_device_check", "ern_l2norm_rows",
     "ern_combiner_packed_bytes", "ern_combiner_pack", "ern_combiner_workspace_bytes", "ern_combiner_forward",
     "ern_sim_topk_workspace_bytes", "ern_sim_topk", "ern_sim_topk_exchange", "ern_topk_merge", "ern_recall_at_k",
-    "ern_cirr_subset_recall",
+    "ern_cirr_subset_recall", "ern_gather_scores", "ern_cirr_subset_from_scores",
     "ern_visualsr_packed_bytes", "ern_visualsr_pack", "ern_visualsr_workspace_bytes", "ern_visualsr_forward",
 )
 
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     l.ern_recall_at_k.argtypes = [vp, i64, i32, vp, i64, vp, C.POINTER(C.c_int32), i32, vp, vp, vp]
     l.ern_cirr_subset_recall.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, i32, vp, vp, i32,
                                          C.POINTER(C.c_int32), i32, vp, vp, vp]
+    l.ern_gather_scores.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i64, vp, i32, vp, vp]
+    l.ern_cirr_subset_from_scores.argtypes = [vp, i64, vp, i32, vp, vp, i32, C.POINTER(C.c_int32), i32, vp, vp, vp]
     l.ern_visualsr_packed_bytes.argtypes = [i32]
     l.ern_visualsr_packed_bytes.restype = sz
     l.ern_visualsr_pack.argtypes = [C.POINTER(VisualSRWeights), i32, vp, vp]

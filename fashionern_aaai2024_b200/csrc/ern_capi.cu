@@ -419,4 +419,27 @@ int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t ldq, con
                             static_cast<cudaStream_t>(stream));
 }
 
+int ern_gather_scores(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
+                      int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* ids_dev, int m,
+                      float* out_scores_dev, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(queries_dev && (gallery_dev || n_rows == 0) && ids_dev && out_scores_dev, "bad arguments");
+  ERN_REQUIRE(dtype == ERN_DTYPE_F32 || dtype == ERN_DTYPE_BF16, "bad dtype");
+  return launch_gather_scores(queries_dev, nq, ldq, gallery_dev, n_rows, ldg, dim, dtype, id_offset, ids_dev, m,
+                              out_scores_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ern_cirr_subset_from_scores(const float* scores_dev, int64_t nq, const int32_t* members_dev, int m,
+                                const int32_t* reference_id_dev, const int32_t* target_id_dev, int rank_by,
+                                const int32_t* ks, int nk, int32_t* counts_dev, int32_t* rank_dev, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  ERN_REQUIRE(scores_dev && members_dev && reference_id_dev && target_id_dev && ks && counts_dev, "bad arguments");
+  return launch_cirr_rank(scores_dev, nq, members_dev, m, reference_id_dev, target_id_dev, rank_by, ks, nk, counts_dev,
+                          rank_dev, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

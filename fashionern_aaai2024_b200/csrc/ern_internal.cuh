@@ -16,6 +16,12 @@ int launch_cirr_subset(const void* queries, int64_t nq, int64_t ldq, const void*
                        int64_t ldg, int dim, int dtype, const int32_t* members, int m, const int32_t* ref_id,
                        const int32_t* tgt_id, int rank_by, const int32_t* ks, int nk, int32_t* counts,
                        int32_t* rank_out, cudaStream_t st);
+int launch_gather_scores(const void* queries, int64_t nq, int64_t ldq, const void* gallery, int64_t n_rows,
+                         int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* ids, int m, float* out,
+                         cudaStream_t st);
+int launch_cirr_rank(const float* scores, int64_t nq, const int32_t* members, int m, const int32_t* ref_id,
+                     const int32_t* tgt_id, int rank_by, const int32_t* ks, int nk, int32_t* counts, int32_t* rank_out,
+                     cudaStream_t st);
 int launch_l2norm_rows(const float* x, int64_t rows, int dim, int64_t ldx, int normalize, float* of, int64_t ldf,
                        void* ob, int64_t ldb, cudaStream_t st);
 

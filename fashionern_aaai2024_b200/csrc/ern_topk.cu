@@ -326,6 +326,92 @@ __global__ void cirr_subset_kernel(const T* __restrict__ queries, int64_t nq, in
   }
 }
 
+// ---- split form for row-sharded galleries: every rank scores the members it owns (0 elsewhere), the caller sums
+//      the [nq, m] matrices over ranks (exactly one owner per member => the sum is exact), then ranks.
+template <typename T>
+__global__ void gather_scores_kernel(const T* __restrict__ queries, int64_t nq, int64_t ldq,
+                                     const T* __restrict__ gallery, int64_t n_rows, int64_t ldg, int dim,
+                                     int64_t id_offset, const int32_t* __restrict__ ids, int m,
+                                     float* __restrict__ out) {
+  const int64_t q = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  for (int j = 0; j < m; ++j) {
+    const int64_t row = static_cast<int64_t>(ids[q * m + j]) - id_offset;
+    float acc = 0.f;
+    if (ids[q * m + j] >= 0 && row >= 0 && row < n_rows) {
+      for (int d = lane; d < dim; d += 32)
+        acc = fmaf(load_as_float(queries, q * ldq + d), load_as_float(gallery, row * ldg + d), acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[q * m + j] = acc;
+  }
+}
+
+__global__ void cirr_rank_kernel(const float* __restrict__ scores, int64_t nq, const int32_t* __restrict__ members,
+                                 int m, const int32_t* __restrict__ ref_id, const int32_t* __restrict__ tgt_id,
+                                 int rank_by, KList kl, int32_t* counts, int32_t* rank_out) {
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q >= nq) return;
+  const int32_t r = ref_id[q], t = tgt_id[q];
+  float val[kMaxMembers];
+  int32_t ids[kMaxMembers];
+  int tpos = -1;
+  for (int j = 0; j < m; ++j) {
+    ids[j] = members[q * m + j];
+    const float s = scores[q * m + j];
+    val[j] = (rank_by == ERN_RANK_REFERENCE) ? -(1.0f - s) : s + 0.0f;
+    if (ids[j] == t && ids[j] != r && ids[j] >= 0) tpos = j;
+  }
+  int rank = -1;
+  if (tpos >= 0) {
+    rank = 0;
+    for (int j = 0; j < m; ++j) {
+      if (j == tpos || ids[j] < 0 || ids[j] == r || ids[j] == t) continue;
+      bool dup = false;
+      for (int i = 0; i < j; ++i) dup |= (ids[i] == ids[j]);
+      if (dup) continue;
+      if (val[j] > val[tpos] || (val[j] == val[tpos] && ids[j] < t)) ++rank;
+    }
+  }
+  if (rank_out) rank_out[q] = rank;
+  if (rank >= 0)
+    for (int i = 0; i < kl.nk; ++i)
+      if (rank < kl.ks[i]) atomicAdd(&counts[i], 1);
+}
+
+int launch_gather_scores(const void* queries, int64_t nq, int64_t ldq, const void* gallery, int64_t n_rows,
+                         int64_t ldg, int dim, int dtype, int64_t id_offset, const int32_t* ids, int m, float* out,
+                         cudaStream_t st) {
+  ERN_REQUIRE(m >= 1 && m <= 64, "m must be in [1,64]");
+  if (nq <= 0) return ERN_OK;
+  const int grid = cdiv(nq * 32, 256);
+  if (dtype == ERN_DTYPE_F32)
+    gather_scores_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(queries), nq, ldq,
+                                                      static_cast<const float*>(gallery), n_rows, ldg, dim, id_offset,
+                                                      ids, m, out);
+  else
+    gather_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(queries), nq, ldq,
+                                                              static_cast<const __nv_bfloat16*>(gallery), n_rows, ldg,
+                                                              dim, id_offset, ids, m, out);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+int launch_cirr_rank(const float* scores, int64_t nq, const int32_t* members, int m, const int32_t* ref_id,
+                     const int32_t* tgt_id, int rank_by, const int32_t* ks, int nk, int32_t* counts, int32_t* rank_out,
+                     cudaStream_t st) {
+  ERN_REQUIRE(nk >= 1 && nk <= kMaxKs, "nk must be in [1,%d]", kMaxKs);
+  ERN_REQUIRE(m >= 1 && m <= kMaxMembers, "group size m must be in [1,%d]", kMaxMembers);
+  KList kl;
+  kl.nk = nk;
+  for (int i = 0; i < nk; ++i) kl.ks[i] = ks[i];
+  zero_i32_kernel<<<1, 32, 0, st>>>(counts, nk);
+  if (nq > 0) cirr_rank_kernel<<<cdiv(nq, 256), 256, 0, st>>>(scores, nq, members, m, ref_id, tgt_id, rank_by, kl, counts, rank_out);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
 int launch_cirr_subset(const void* queries, int64_t nq, int64_t ldq, const void* gallery, int64_t n_rows,
                        int64_t ldg, int dim, int dtype, const int32_t* members, int m, const int32_t* ref_id,
                        const int32_t* tgt_id, int rank_by, const int32_t* ks, int nk, int32_t* counts,

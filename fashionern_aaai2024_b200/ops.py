@@ -14,7 +14,8 @@ from . import _lib as L
 from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MAX_K, MODE_BF16, MODE_FP32, RANK_REFERENCE,
                    RANK_SIMILARITY, SORT_CAP, ErnError)
 
-__all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "launch_counter"]
+__all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "gather_scores",
+           "cirr_subset_from_scores", "launch_counter"]
 
 
 class _LaunchCounter:
@@ -218,5 +219,45 @@ def cirr_subset_recall(queries: torch.Tensor, gallery: torch.Tensor, members: to
                                                q.shape[1], dtype, members.data_ptr(), m, reference_ids.data_ptr(),
                                                target_ids.data_ptr(), rank_by, arr, nk, counts.data_ptr(),
                                                ranks.data_ptr(), L.stream_ptr(dev)))
+    launch_counter.add(2 if nq else 1)
+    return counts, ranks
+
+
+def gather_scores(queries: torch.Tensor, gallery: torch.Tensor, ids: torch.Tensor, id_offset: int = 0) -> torch.Tensor:
+    """Similarity of query q with the gallery rows ``ids[q, :]`` (global ids) that live in this shard
+    (rows ``[id_offset, id_offset + len(gallery))``); 0 for rows owned by another shard, so that a SUM over the
+    shards gives the full [Q, m] matrix (CIRR group-member scores gathered from the owning shards)."""
+    q = _rowmajor(queries, "queries")
+    g = _rowmajor(gallery, "gallery")
+    if q.dtype != g.dtype or q.dtype not in (torch.float32, torch.bfloat16):
+        raise ErnError("queries/gallery must both be float32 or both bfloat16")
+    ids = ids.to(torch.int32).contiguous()
+    nq, m = ids.shape
+    out = torch.empty((nq, m), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        L.check(L.lib().ern_gather_scores(q.data_ptr(), nq, q.stride(0), g.data_ptr(), g.shape[0], g.stride(0), q.shape[1],
+                                          DTYPE_F32 if q.dtype == torch.float32 else DTYPE_BF16, int(id_offset),
+                                          ids.data_ptr(), m, out.data_ptr(), L.stream_ptr(q.device)))
+    launch_counter.add(1 if nq else 0)
+    return out
+
+
+def cirr_subset_from_scores(scores: torch.Tensor, members: torch.Tensor, reference_ids: torch.Tensor,
+                            target_ids: torch.Tensor, ks: Sequence[int] = (1, 2, 3), rank_by: int = RANK_REFERENCE):
+    """CIRR subset recall (run/test/test_cirr.py:64-66,76-78) from already gathered member similarities [Q, m]."""
+    L.require_cuda(scores, "scores")
+    scores = scores.float().contiguous()
+    members = members.to(torch.int32).contiguous()
+    reference_ids = reference_ids.to(torch.int32).contiguous()
+    target_ids = target_ids.to(torch.int32).contiguous()
+    nq, m = members.shape
+    dev = scores.device
+    counts = torch.empty(len(ks), dtype=torch.int32, device=dev)
+    ranks = torch.empty(nq, dtype=torch.int32, device=dev)
+    arr, nk = _ks(ks)
+    with torch.cuda.device(dev):
+        L.check(L.lib().ern_cirr_subset_from_scores(scores.data_ptr(), nq, members.data_ptr(), m, reference_ids.data_ptr(),
+                                                    target_ids.data_ptr(), rank_by, arr, nk, counts.data_ptr(),
+                                                    ranks.data_ptr(), L.stream_ptr(dev)))
     launch_counter.add(2 if nq else 1)
     return counts, ranks

@@ -94,3 +94,25 @@ def sharded_topk(queries: torch.Tensor, local_gallery: torch.Tensor, k: int, id_
         return (*ops.topk_merge(keys.unsqueeze(0), k), status)
     gathered = exchange_candidates(keys, group)
     return (*ops.topk_merge(gathered, k), status)
+
+
+def sharded_recall(queries: torch.Tensor, local_gallery: torch.Tensor, id_offset: int, class_of: torch.Tensor,
+                   target_class: torch.Tensor, ks, *, mode: int = MODE_BF16, rank_by: int = RANK_SIMILARITY,
+                   exclude_ids: Optional[torch.Tensor] = None, group=None, exchange: str = "nccl"):
+    """Recall@K hit counts over a row-sharded gallery: global top-max(ks) (identical on every rank) followed by the
+    id-membership kernel against the replicated ``class_of`` table (int32 [N_total]).  Returns (counts, ranks, ids)."""
+    _, ids, _, _ = sharded_topk(queries, local_gallery, int(max(ks)), id_offset, mode=mode, rank_by=rank_by,
+                                exclude_ids=exclude_ids, group=group, exchange=exchange)
+    counts, ranks = ops.recall_at_k(ids, class_of, target_class, ks)
+    return counts, ranks, ids
+
+
+def sharded_cirr_subset(queries: torch.Tensor, local_gallery: torch.Tensor, id_offset: int, members: torch.Tensor,
+                        reference_ids: torch.Tensor, target_ids: torch.Tensor, ks=(1, 2, 3), *, rank_by: int = 1,
+                        group=None):
+    """CIRR subset recall when the group members' rows are spread over the shards: each rank scores
+    the members it owns, one all-reduce(SUM) of the [Q, 6] matrix assembles them, every rank ranks identically."""
+    scores = ops.gather_scores(queries, local_gallery, members, id_offset)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(scores, op=dist.ReduceOp.SUM, group=group)
+    return ops.cirr_subset_from_scores(scores, members, reference_ids, target_ids, ks, rank_by=rank_by)

@@ -211,6 +211,20 @@ ERN_API int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t 
                            const int32_t* target_id_dev, int rank_by, const int32_t* ks, int nk,
                            int32_t* counts_dev, int32_t* rank_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Split form of the CIRR subset recall for row-sharded galleries: every rank scores the
+ * group members whose rows it owns -- out[q,j] = <query q, gallery row ids[q,j] - id_offset> or 0 when the
+ * row is not in [id_offset, id_offset + n_rows) -- the caller sums the [nq,m] matrices over the ranks
+ * (one owner per member, so the sum is exact) and ranks with ern_cirr_subset_from_scores.
+ * ------------------------------------------------------------------------------------------- */
+ERN_API int ern_gather_scores(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,
+                      int64_t n_rows, int64_t ldg, int dim, int dtype, int64_t id_offset,
+                      const int32_t* ids_dev, int m, float* out_scores_dev, void* stream);
+ERN_API int ern_cirr_subset_from_scores(const float* scores_dev, int64_t nq, const int32_t* members_dev, int m,
+                                const int32_t* reference_id_dev, const int32_t* target_id_dev,
+                                int rank_by, const int32_t* ks, int nk, int32_t* counts_dev,
+                                int32_t* rank_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

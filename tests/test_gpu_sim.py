@@ -162,3 +162,22 @@ def test_large_gallery_bf16_subset_parity(cuda_device):
     sub = torch.arange(0, q, 64)
     orc.compare_topk(ids[sub.to(cuda_device)].cpu().numpy(), None, pred[sub.to(cuda_device)].float().cpu(),
                      gal.float().cpu(), k, tol=TOL_BF16_SAME_INPUTS)
+
+
+def test_split_cirr_subset_equals_fused(cuda_device):
+    # shard-emulation on one GPU: member scores gathered shard by shard and summed == the fused kernel
+    q, n, dim = 300, 2000, 640
+    pred, gal = unit(51, q, dim).to(cuda_device), unit(52, n, dim).to(cuda_device)
+    g = torch.Generator().manual_seed(53)
+    members = torch.stack([torch.randperm(n, generator=g)[:6] for _ in range(q)]).int().to(cuda_device)
+    ref, tgt = members[:, 0].contiguous(), members[:, 1].contiguous()
+    members = members[:, torch.randperm(6, generator=g)].contiguous()
+    for cast in (torch.float32, torch.bfloat16):
+        p, G = pred.to(cast), gal.to(cast)
+        c_f, r_f = ops.cirr_subset_recall(p, G, members, ref, tgt, (1, 2, 3))
+        total = torch.zeros(q, 6, device=cuda_device)
+        for a, b in ((0, 700), (700, 701), (701, 2000)):
+            total += ops.gather_scores(p, G[a:b], members, id_offset=a)
+        c_s, r_s = ops.cirr_subset_from_scores(total, members, ref, tgt, (1, 2, 3))
+        assert torch.equal(r_f, r_s) and torch.equal(c_f, c_s)
+        assert bool((r_s >= 0).all()) and 0 < int(c_s[0]) < q
