@@ -1,0 +1,60 @@
+"""CPU (+ one GPU case): packed feature store round trip, sharded loader coverage, id gathers."""
+import numpy as np
+import pytest
+import torch
+
+from fashionern_aaai2024_b200 import synthetic as syn
+from fashionern_aaai2024_b200.sharded import shard_bounds
+from fashionern_aaai2024_b200.store import FeatureStore
+
+
+def make(tmp_path, n=1000, dim=64, patches=13):
+    feats = syn.features(1, n, dim, unit=True)
+    local = syn.patch_features(2, n, dim, patches)
+    names = syn.caption_names(3, n, 50)
+    return FeatureStore.save(str(tmp_path / "store"), feats, names, local, chunk_rows=300), feats, local, names
+
+
+def test_round_trip_is_bit_exact_bf16(tmp_path):
+    st, feats, local, names = make(tmp_path)
+    assert (st.rows, st.dim, st.patches) == (1000, 64, 13) and st.names == names
+    whole, off = st.load_shard(0, 1, device="cpu", chunk_rows=128)
+    assert off == 0 and torch.equal(whole, feats.bfloat16())
+    rows = [5, 999, 0, 5]
+    assert torch.equal(st.gather(rows, device="cpu"), feats.bfloat16()[rows])
+    assert torch.equal(st.load_local(rows, device="cpu"), local.bfloat16()[rows])
+    m = st.name_to_row()
+    assert all(names[m[nm]] == nm for nm in set(names)) and m[names[-1]] == 999   # repeated name -> last row
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shards_tile_the_gallery(tmp_path, world):
+    st, feats, *_ = make(tmp_path, n=1001)
+    parts, offs = zip(*[st.load_shard(r, world, device="cpu", chunk_rows=97) for r in range(world)])
+    assert [o for o in offs] == [shard_bounds(1001, world, r)[0] for r in range(world)]
+    assert torch.equal(torch.cat(parts), feats.bfloat16())
+
+
+def test_empty_and_bad_store(tmp_path):
+    st = FeatureStore.save(str(tmp_path / "e"), torch.zeros(0, 64))
+    g, off = st.load_shard(0, 2, device="cpu")
+    assert g.shape == (0, 64) and off == 0
+    with pytest.raises(ValueError):
+        st.load_local([0])
+    with pytest.raises(ValueError):
+        FeatureStore.save(str(tmp_path / "b"), torch.zeros(3, 8), names=["a"])
+
+
+@pytest.mark.gpu
+def test_shard_feeds_the_scoring_kernel(tmp_path, cuda_device):
+    from fashionern_aaai2024_b200 import ops
+    n, dim, k = 5000, 640, 20
+    feats = syn.features(9, n, dim, unit=True)
+    st = FeatureStore.save(str(tmp_path / "g"), feats)
+    pred = syn.features(10, 64, dim, unit=True).bfloat16().to(cuda_device)
+    full = ops.sim_topk(pred, feats.bfloat16().to(cuda_device), k, want_keys=True)[2]
+    parts = []
+    for r in range(3):
+        shard, off = st.load_shard(r, 3, device=cuda_device, chunk_rows=512)
+        parts.append(ops.sim_topk(pred, shard, k, id_offset=off, want_keys=True)[2])
+    assert torch.equal(ops.topk_merge(torch.stack(parts), k)[2], full)
