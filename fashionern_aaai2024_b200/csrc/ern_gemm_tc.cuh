@@ -259,10 +259,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <int kBlockN, int kEpi>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const Params& p, int sm_count, cudaStream_t st) {
   auto kern = gemm_tc_kernel<kBlockN, kEpi>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in shared-memory size is a per-device function attribute
+  static bool configured[64] = {};
+  int dev = 0;
+  ERN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kBlockN>()));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   const int64_t tiles = ((p.m + kBlockM - 1) / kBlockM) * (p.n / kBlockN);
   const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);

@@ -322,10 +322,13 @@ int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int di
 template <bool kPair, int kRankBy>
 static int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const Params& p, int grid, cudaStream_t st) {
   auto kern = sim_topk_tc_kernel<kPair, kRankBy>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in shared-memory size is a per-device function attribute
+  static bool configured[64] = {};
+  int dev = 0;
+  ERN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
