@@ -14,6 +14,7 @@ All compute is hand-written CUDA behind ``libern_b200.so``; there is no CPU or t
 from ._lib import ErnError, MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARITY  # noqa: F401
 from .combiner import CombinerSimple, accelerate_ern  # noqa: F401
 from .visual_sr import VisualSR  # noqa: F401
+from .dvr import DVR_module  # noqa: F401
 from . import ops, sharded, store  # noqa: F401
 from .metrics import (compute_200k_val_metrics, compute_cirr_val_metrics, compute_fiq_val_metrics,  # noqa: F401
                       compute_shoes_val_metrics, compute_val_metrics, score_topk_recall, set_precision,

@@ -28,6 +28,7 @@ SYMBOLS = (
     "ern_sim_topk_workspace_bytes", "ern_sim_topk", "ern_sim_topk_exchange", "ern_topk_merge", "ern_recall_at_k",
     "ern_cirr_subset_recall", "ern_gather_scores", "ern_cirr_subset_from_scores",
     "ern_visualsr_packed_bytes", "ern_visualsr_pack", "ern_visualsr_workspace_bytes", "ern_visualsr_forward",
+    "ern_dvr_packed_bytes", "ern_dvr_pack", "ern_dvr_workspace_bytes", "ern_dvr_encode",
 )
 
 
@@ -44,6 +45,17 @@ class VisualSRWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w_local", "b_local", "bn_local_scale", "bn_local_shift", "w_global",
                                           "b_global", "bn_global_scale", "bn_global_shift", "w_common", "b_common",
                                           "packed_bf16")]
+
+
+class BertLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln1_w", "ln1_b", "wi", "bi",
+                                          "wo2", "bo2", "ln2_w", "ln2_b")]
+
+
+class DvrWeights(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("cls_token", "pos_emb", "type_emb", "emb_ln_w", "emb_ln_b")]
+                + [("n_layers", C.c_int), ("intermediate", C.c_int), ("layers", BertLayerWeights * 4)]
+                + [(n, C.c_void_p) for n in ("mha_in_w", "mha_in_b", "mha_out_w", "mha_out_b", "packed_bf16")])
 
 
 _lib: Optional[C.CDLL] = None
@@ -87,6 +99,12 @@ def lib() -> C.CDLL:
     l.ern_visualsr_workspace_bytes.argtypes = [i64, i32, i32, i32]
     l.ern_visualsr_workspace_bytes.restype = sz
     l.ern_visualsr_forward.argtypes = [C.POINTER(VisualSRWeights), i32, i32, i32, vp, i64, vp, vp, sz, vp]
+    l.ern_dvr_packed_bytes.argtypes = [i32, i32, i32]
+    l.ern_dvr_packed_bytes.restype = sz
+    l.ern_dvr_pack.argtypes = [C.POINTER(DvrWeights), i32, vp, vp]
+    l.ern_dvr_workspace_bytes.argtypes = [i64, i32, i32, i32, i32, i32]
+    l.ern_dvr_workspace_bytes.restype = sz
+    l.ern_dvr_encode.argtypes = [C.POINTER(DvrWeights), i32, i32, i32, i32, i32, vp, vp, i64, vp, vp, vp, sz, vp]
     for name in SYMBOLS:
         fn = getattr(l, name)
         if fn.restype is C.c_int and name not in ("ern_version",):

@@ -114,11 +114,17 @@ class CombinerSimple(nn.Module):
 def accelerate_ern(model: nn.Module, mode: str = "bf16") -> nn.Module:
     """Swap every reference ``CombinerSimple`` inside an ``ERN`` (models/model.py:16-20: ``DVR.combiner_global``,
     ``DVR.combiner_local``, ``DVR.combiner``, ``Combiner_module``) and every reference ``VisualSR`` (``SR_module``,
-    ``DVR.SR_module``) for the B200 modules, keeping their weights and buffers."""
+    ``DVR.SR_module``) and the whole query-side ``DVR_module`` (``DVR``) for the B200 modules, keeping their weights
+    and buffers."""
+    from .dvr import DVR_module
     from .visual_sr import VisualSR
     for name, child in list(model.named_children()):
         cls = type(child).__name__
-        if cls == "CombinerSimple" and not isinstance(child, CombinerSimple) and hasattr(child, "dynamic_scalar"):
+        if cls == "DVR_module" and not isinstance(child, DVR_module) and hasattr(child, "MR_component"):
+            dim = child.MR_component.embed_dim
+            new = DVR_module(dim, device=None, layers=len(child.transformer_layer.bert_encoder.bert_model.encoder.layer),
+                             mode=mode)
+        elif cls == "CombinerSimple" and not isinstance(child, CombinerSimple) and hasattr(child, "dynamic_scalar"):
             dim = child.text_projection_layer[0].in_features
             new = CombinerSimple(dim, dim * 4, dim * 8, mode=mode)
         elif cls == "VisualSR" and not isinstance(child, VisualSR) and hasattr(child, "embedding_common"):

@@ -179,6 +179,68 @@ int ern_combiner_forward(const ern_combiner_weights* w, int dim, int mode, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+size_t ern_dvr_packed_bytes(int dim, int intermediate, int n_layers) {
+  if (dim <= 0 || intermediate <= 0 || n_layers < 0) return 0;
+  return dvr::packed_bytes(dim, intermediate, n_layers);
+}
+
+static int check_dvr_weights(const ern_dvr_weights* w) {
+  ERN_REQUIRE(w && w->cls_token && w->pos_emb && w->type_emb && w->emb_ln_w && w->emb_ln_b, "embedding tensors missing");
+  ERN_REQUIRE(w->n_layers >= 0 && w->n_layers <= ERN_MAX_BERT_LAYERS, "n_layers must be in [0,%d]", ERN_MAX_BERT_LAYERS);
+  ERN_REQUIRE(w->intermediate > 0, "intermediate size missing");
+  for (int i = 0; i < w->n_layers; ++i) {
+    const ern_bert_layer_weights& l = w->layers[i];
+    ERN_REQUIRE(l.wq && l.bq && l.wk && l.bk && l.wv && l.bv && l.wo && l.bo && l.ln1_w && l.ln1_b && l.wi && l.bi &&
+                    l.wo2 && l.bo2 && l.ln2_w && l.ln2_b,
+                "layer %d: parameter tensor missing", i);
+  }
+  ERN_REQUIRE(w->mha_in_w && w->mha_in_b && w->mha_out_w && w->mha_out_b, "MR_component tensors missing");
+  return ERN_OK;
+}
+
+int ern_dvr_pack(const ern_dvr_weights* w, int dim, void* packed_dev, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  if ((rc = check_dvr_weights(w))) return rc;
+  ERN_REQUIRE(packed_dev && dim > 0, "bad arguments");
+  return dvr::pack(w, dim, packed_dev, static_cast<cudaStream_t>(stream));
+}
+
+size_t ern_dvr_workspace_bytes(int64_t batch, int patches, int tokens, int dim, int intermediate, int mode) {
+  if (batch < 0 || patches <= 0 || tokens <= 0 || dim <= 0 || intermediate <= 0) return 0;
+  return dvr::workspace_bytes(batch, patches, tokens, dim, intermediate, mode);
+}
+
+int ern_dvr_encode(const ern_dvr_weights* w, int dim, int heads, int patches, int tokens, int mode,
+                   const float* patches_dev, const float* tokens_dev, int64_t batch, float* out_cross_dev,
+                   float* out_seq_mean_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  if ((rc = check_dvr_weights(w))) return rc;
+  ERN_REQUIRE(patches_dev && tokens_dev && out_cross_dev && out_seq_mean_dev && batch >= 0, "bad arguments");
+  ERN_REQUIRE(dim > 0 && dim <= 1024 && heads > 0 && dim % heads == 0, "dim must be <= 1024 and divisible by heads");
+  ERN_REQUIRE(patches >= 1 && tokens >= patches && 1 + patches + tokens <= 512,
+              "need 1 <= patches <= tokens and 1 + patches + tokens <= 512 (position table)");
+  ERN_REQUIRE(mode == ERN_MODE_FP32 || mode == ERN_MODE_BF16, "unknown mode %d", mode);
+  if (mode == ERN_MODE_BF16) {
+    ERN_REQUIRE(w->packed_bf16, "bf16 mode needs packed weights (ern_dvr_pack)");
+    if (dim % 128 != 0 || w->intermediate % 128 != 0) {
+      set_error("bf16 DVR encoder needs dim %% 128 == 0 and intermediate %% 128 == 0 (got %d, %d)", dim, w->intermediate);
+      return ERN_ERR_UNSUPPORTED;
+    }
+  }
+  const size_t need = ern_dvr_workspace_bytes(batch, patches, tokens, dim, w->intermediate, mode);
+  if (workspace_bytes < need || (!workspace_dev && batch > 0)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return ERN_ERR_WORKSPACE;
+  }
+  return dvr::encode(w, dim, heads, patches, tokens, mode, patches_dev, tokens_dev, batch, out_cross_dev,
+                     out_seq_mean_dev, workspace_dev, di.sm_count, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 size_t ern_visualsr_packed_bytes(int dim) { return visualsr::packed_bytes(dim); }
 
 int ern_visualsr_pack(const ern_visualsr_weights* w, int dim, void* packed_dev, void* stream) {

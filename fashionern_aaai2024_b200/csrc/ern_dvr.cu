@@ -1,0 +1,400 @@
+// Query-side encoder of DVR_module (models/fusion_model.py:26-49) -- SURVEY.md 8(f) "next" row 2:
+//   PlusModel (:187-216): [CLS] + 13 patch embeddings + 77 token embeddings -> HF BERT encoder (2 layers, 8 heads,
+//   intermediate 3072, erf-GELU, LayerNorm eps 1e-12, absolute position + token-type embeddings, all-ones mask)
+//   F.normalize of the patch / token states (:38-41), nn.MultiheadAttention cross attention text -> patches (:44-46)
+//   of which only the first 13 query positions are used (:47), and the mean of the normalised token states (:49).
+// Outputs: cross_vision_feats[:, :13] (input of SR_module) and seq_text_mean (input of combiner_local).
+// Every GEMM runs on the tensor-core kernel of ern_gemm_tc.cuh (bf16 mode) or the FFMA kernel of ern_gemm_f32.cuh
+// (fp32 validation mode); embeddings+LayerNorm, attention (L = 91 per head: CUDA cores, fp32 math), row-normalise and
+// LayerNorm are small dedicated kernels.  Eval mode only (dropouts are identities).
+#include "ern_gemm_f32.cuh"
+#include "ern_gemm_tc.cuh"
+
+namespace ern {
+namespace dvr {
+
+constexpr int kMaxPerLane = 32;  // D <= 1024
+constexpr float kLnEps = 1e-12f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// LayerNorm of one row held as v[i] = x[lane + 32 i]; two-pass (mean, then centred variance) like torch
+__device__ __forceinline__ void layer_norm_row(float (&v)[kMaxPerLane], int dim, int lane, const float* w,
+                                               const float* b, float* out, __nv_bfloat16* out_b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (lane + 32 * i < dim) s += v[i];
+  const float mean = warp_sum(s) / static_cast<float>(dim);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i)
+    if (lane + 32 * i < dim) {
+      const float c = v[i] - mean;
+      ss = fmaf(c, c, ss);
+    }
+  const float rstd = rsqrtf(warp_sum(ss) / static_cast<float>(dim) + kLnEps);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim) {
+      const float y = (v[i] - mean) * rstd * w[d] + b[d];
+      if (out) out[d] = y;
+      if (out_b) out_b[d] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// one warp per token row: inputs_embeds + token_type + position -> LayerNorm  (HF BertEmbeddings with inputs_embeds)
+__global__ void embed_ln_kernel(const float* __restrict__ patches, const float* __restrict__ tokens,
+                                const float* __restrict__ cls, const float* __restrict__ pos,
+                                const float* __restrict__ type, const float* __restrict__ w,
+                                const float* __restrict__ b, int64_t batch, int P, int T, int dim,
+                                float* __restrict__ X, __nv_bfloat16* __restrict__ Xb) {
+  const int L = 1 + P + T;
+  const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= batch * L) return;
+  const int64_t bi = r / L;
+  const int t = static_cast<int>(r % L);
+  const float* src = t == 0 ? cls : (t <= P ? patches + (bi * P + (t - 1)) * dim : tokens + (bi * T + (t - 1 - P)) * dim);
+  const float* ty = type + (t <= P ? 0 : dim);
+  float v[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int d = lane + 32 * i;
+    v[i] = d < dim ? src[d] + ty[d] + pos[static_cast<int64_t>(t) * dim + d] : 0.f;
+  }
+  layer_norm_row(v, dim, lane, w, b, X + r * dim, Xb ? Xb + r * dim : nullptr);
+}
+
+__global__ void layernorm_kernel(const float* __restrict__ in, int64_t rows, int dim, const float* __restrict__ w,
+                                 const float* __restrict__ b, float* __restrict__ out, __nv_bfloat16* __restrict__ out_b) {
+  const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float v[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int d = lane + 32 * i;
+    v[i] = d < dim ? in[r * dim + d] : 0.f;
+  }
+  layer_norm_row(v, dim, lane, w, b, out + r * dim, out_b ? out_b + r * dim : nullptr);
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// softmax(Q K^T * scale) V for one (batch element, head); sequences are short (<= 91), everything lives in smem
+template <typename T>
+__global__ void __launch_bounds__(256)
+attention_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ K, int64_t ldk, const T* __restrict__ V,
+                 int64_t ldv, T* __restrict__ O, int64_t ldo, int Lq, int Lk, int dh, float scale) {
+  extern __shared__ float sm[];
+  const int h = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int pitch = dh + 1;
+  float* Qs = sm;
+  float* Ks = Qs + Lq * pitch;
+  float* Vs = Ks + Lk * pitch;
+  float* S = Vs + Lk * pitch;   // [Lq][Lk + 1]
+  const int sp = Lk + 1;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < Lq * dh; e += 256) {
+    const int i = e / dh, d = e % dh;
+    Qs[i * pitch + d] = to_f(Q[(b * Lq + i) * ldq + h * dh + d]);
+  }
+  for (int e = tid; e < Lk * dh; e += 256) {
+    const int j = e / dh, d = e % dh;
+    Ks[j * pitch + d] = to_f(K[(b * Lk + j) * ldk + h * dh + d]);
+    Vs[j * pitch + d] = to_f(V[(b * Lk + j) * ldv + h * dh + d]);
+  }
+  __syncthreads();
+  for (int e = tid; e < Lq * Lk; e += 256) {
+    const int i = e / Lk, j = e % Lk;
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(Qs[i * pitch + d], Ks[j * pitch + d], acc);
+    S[i * sp + j] = acc * scale;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int i = warp; i < Lq; i += 8) {
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, S[i * sp + j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float ev = expf(S[i * sp + j] - mx);
+      S[i * sp + j] = ev;
+      sum += ev;
+    }
+    sum = warp_sum(sum);
+    for (int j = lane; j < Lk; j += 32) S[i * sp + j] = S[i * sp + j] / sum;
+  }
+  __syncthreads();
+  for (int e = tid; e < Lq * dh; e += 256) {
+    const int i = e / dh, d = e % dh;
+    float acc = 0.f;
+    for (int j = 0; j < Lk; ++j) acc = fmaf(S[i * sp + j], Vs[j * pitch + d], acc);
+    O[(b * Lq + i) * ldo + h * dh + d] = from_f<T>(acc);
+  }
+}
+
+// One block per batch element: F.normalize of the patch / token states (models/fusion_model.py:38-41), the first P
+// normalised token rows (the only cross-attention queries used, :47) and seq_text_mean (:49).
+template <typename T>
+__global__ void __launch_bounds__(256)
+post_kernel(const float* __restrict__ X, int P, int Tn, int dim, T* __restrict__ image_norm, T* __restrict__ text_first,
+            float* __restrict__ seq_text_mean) {
+  __shared__ float partial[8][1024];
+  const int64_t b = blockIdx.x;
+  const int L = 1 + P + Tn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float accum[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) accum[i] = 0.f;
+  for (int t = 1 + warp; t < L; t += 8) {
+    const float* x = X + (b * L + t) * dim;
+    float v[kMaxPerLane];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int d = lane + 32 * i;
+      v[i] = d < dim ? x[d] : 0.f;
+      ss = fmaf(v[i], v[i], ss);
+    }
+    const float denom = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int d = lane + 32 * i;
+      if (d >= dim) continue;
+      const float y = v[i] / denom;
+      if (t <= P) {
+        image_norm[(b * P + (t - 1)) * dim + d] = from_f<T>(y);
+      } else {
+        accum[i] += y;
+        if (t - 1 - P < P) text_first[(b * P + (t - 1 - P)) * dim + d] = from_f<T>(y);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim) partial[warp][d] = accum[i];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < dim; d += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += partial[w8][d];   // fixed order: deterministic
+    seq_text_mean[b * dim + d] = s / static_cast<float>(Tn);
+  }
+}
+
+// ---- packed bf16 weights: per layer wq wk wv wo (DxD), wi (IxD), wo2 (DxI); then mha_in (3DxD), mha_out (DxD) --------
+static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
+struct PackedLayout {
+  size_t layer_stride, wq, wk, wv, wo, wi, wo2, mha_in, mha_out, total;
+};
+static PackedLayout layout(int dim, int inter, int n_layers) {
+  PackedLayout l;
+  const size_t d = dim, I = inter;
+  l.wq = 0;
+  l.wk = al(d * d * 2);
+  l.wv = 2 * al(d * d * 2);
+  l.wo = 3 * al(d * d * 2);
+  l.wi = 4 * al(d * d * 2);
+  l.wo2 = l.wi + al(I * d * 2);
+  l.layer_stride = l.wo2 + al(d * I * 2);
+  l.mha_in = l.layer_stride * n_layers;
+  l.mha_out = l.mha_in + al(3 * d * d * 2);
+  l.total = l.mha_out + al(d * d * 2) + 256;
+  return l;
+}
+
+size_t packed_bytes(int dim, int inter, int n_layers) { return layout(dim, inter, n_layers).total; }
+
+int pack(const ern_dvr_weights* w, int dim, void* packed, cudaStream_t st) {
+  const PackedLayout l = layout(dim, w->intermediate, w->n_layers);
+  uint8_t* p = static_cast<uint8_t*>(packed);
+  const int64_t dd = static_cast<int64_t>(dim) * dim, di = static_cast<int64_t>(dim) * w->intermediate;
+  int rc = 0;
+  for (int i = 0; i < w->n_layers && !rc; ++i) {
+    const ern_bert_layer_weights& lw = w->layers[i];
+    uint8_t* b = p + l.layer_stride * i;
+    if (!rc) rc = combiner::launch_cast_bf16(lw.wq, b + l.wq, dd, st);
+    if (!rc) rc = combiner::launch_cast_bf16(lw.wk, b + l.wk, dd, st);
+    if (!rc) rc = combiner::launch_cast_bf16(lw.wv, b + l.wv, dd, st);
+    if (!rc) rc = combiner::launch_cast_bf16(lw.wo, b + l.wo, dd, st);
+    if (!rc) rc = combiner::launch_cast_bf16(lw.wi, b + l.wi, di, st);
+    if (!rc) rc = combiner::launch_cast_bf16(lw.wo2, b + l.wo2, di, st);
+  }
+  if (!rc) rc = combiner::launch_cast_bf16(w->mha_in_w, p + l.mha_in, 3 * dd, st);
+  if (!rc) rc = combiner::launch_cast_bf16(w->mha_out_w, p + l.mha_out, dd, st);
+  return rc;
+}
+
+// ---- workspace ------------------------------------------------------------------------------------------------------
+struct Work {
+  float *X, *Y, *seq_dummy;
+  uint8_t *Xb, *QKV, *CTX, *H, *img, *txt, *mq, *mkv, *mctx;
+  size_t total;
+};
+static Work carve(void* base, int64_t batch, int P, int T, int dim, int inter, int mode) {
+  const size_t es = mode == ERN_MODE_FP32 ? 4 : 2;
+  const size_t M = static_cast<size_t>(batch) * (1 + P + T), MP = static_cast<size_t>(batch) * P, d = dim, I = inter;
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t off = 0;
+  Work w;
+  auto take = [&](size_t bytes) { uint8_t* r = p + off; off += al(bytes); return r; };
+  w.X = reinterpret_cast<float*>(take(M * d * 4));
+  w.Y = reinterpret_cast<float*>(take(M * d * 4));
+  w.Xb = take(mode == ERN_MODE_FP32 ? 0 : M * d * 2);
+  w.QKV = take(M * 3 * d * es);
+  w.CTX = take(M * d * es);
+  w.H = take(M * I * es);
+  w.img = take(MP * d * es);
+  w.txt = take(MP * d * es);
+  w.mq = take(MP * d * es);
+  w.mkv = take(MP * 2 * d * es);
+  w.mctx = take(MP * d * es);
+  w.total = off + 256;
+  return w;
+}
+
+size_t workspace_bytes(int64_t batch, int P, int T, int dim, int inter, int mode) {
+  return carve(nullptr, batch, P, T, dim, inter, mode).total;
+}
+
+template <typename T>
+static int run_attention(const T* Q, int64_t ldq, const T* K, int64_t ldk, const T* V, int64_t ldv, T* O, int64_t ldo,
+                         int64_t batch, int heads, int Lq, int Lk, int dh, cudaStream_t st) {
+  const size_t smem = (static_cast<size_t>(Lq + 2 * Lk) * (dh + 1) + static_cast<size_t>(Lq) * (Lk + 1)) * 4;
+  auto kern = attention_kernel<T>;
+  static size_t configured[64] = {};
+  int dev = 0;
+  ERN_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && configured[dev] < smem) {
+    ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured[dev] = smem;
+  }
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    kern<<<dim3(heads, static_cast<unsigned>(nb)), 256, smem, st>>>(Q + b0 * Lq * ldq, ldq, K + b0 * Lk * ldk, ldk,
+                                                                   V + b0 * Lk * ldv, ldv, O + b0 * Lq * ldo, ldo, Lq, Lk,
+                                                                   dh, 1.0f / sqrtf(static_cast<float>(dh)));
+  }
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+// bf16 GEMM helper: out = epilogue(A[M,K] . W[N,K]^T)
+template <int kEpi>
+static int tc_gemm(const void* A, int64_t M, int K, const void* W, int N, const float* bias, __nv_bfloat16* out_b,
+                   int64_t ldo, int col0, float* out_f, const float* residual, int sm_count, cudaStream_t st) {
+  CUtensorMap ta, tw;
+  int rc;
+  if ((rc = simtc::make_tmap_bf16_rows(&ta, A, M, K, K))) return rc;
+  if ((rc = simtc::make_tmap_bf16_rows(&tw, W, N, K, K))) return rc;
+  gemmtc::Params p{};
+  p.m = M;
+  p.n = N;
+  p.k = K;
+  p.bias = bias;
+  p.out = out_b;
+  p.ldo = ldo;
+  p.col0 = col0;
+  p.out_f32 = out_f;
+  p.residual = residual;
+  return gemmtc::launch<128, kEpi>(ta, tw, p, sm_count, st);
+}
+
+int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode, const float* patches,
+           const float* tokens, int64_t batch, float* out_cross, float* out_seq_mean, void* workspace, int sm_count,
+           cudaStream_t st) {
+  if (batch <= 0) return ERN_OK;
+  const int L = 1 + P + T, I = w->intermediate, dh = dim / heads;
+  const int64_t M = batch * L, MP = batch * P;
+  const bool f32 = mode == ERN_MODE_FP32;
+  Work ws = carve(workspace, batch, P, T, dim, I, mode);
+  const int wb_rows = cdiv(M * 32, 256);
+  int rc = 0;
+  __nv_bfloat16* Xb = f32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(ws.Xb);
+  embed_ln_kernel<<<wb_rows, 256, 0, st>>>(patches, tokens, w->cls_token, w->pos_emb, w->type_emb, w->emb_ln_w,
+                                           w->emb_ln_b, batch, P, T, dim, ws.X, Xb);
+  ERN_CUDA(cudaGetLastError());
+  const PackedLayout pl = layout(dim, I, w->n_layers);
+  const uint8_t* pk = static_cast<const uint8_t*>(w->packed_bf16);
+
+  for (int li = 0; li < w->n_layers; ++li) {
+    const ern_bert_layer_weights& lw = w->layers[li];
+    if (f32) {
+      float* qkv = reinterpret_cast<float*>(ws.QKV);
+      float* ctx = reinterpret_cast<float*>(ws.CTX);
+      float* hbuf = reinterpret_cast<float*>(ws.H);
+      if ((rc = gemmf32::launch<gemmf32::kActNone>(ws.X, dim, M, lw.wq, dim, dim, lw.bq, nullptr, qkv, 3 * dim, st))) return rc;
+      if ((rc = gemmf32::launch<gemmf32::kActNone>(ws.X, dim, M, lw.wk, dim, dim, lw.bk, nullptr, qkv + dim, 3 * dim, st))) return rc;
+      if ((rc = gemmf32::launch<gemmf32::kActNone>(ws.X, dim, M, lw.wv, dim, dim, lw.bv, nullptr, qkv + 2 * dim, 3 * dim, st))) return rc;
+      if ((rc = run_attention<float>(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ctx, dim, batch, heads, L, L, dh, st))) return rc;
+      if ((rc = gemmf32::launch<gemmf32::kActNone>(ctx, dim, M, lw.wo, dim, dim, lw.bo, ws.X, ws.Y, dim, st))) return rc;
+      layernorm_kernel<<<wb_rows, 256, 0, st>>>(ws.Y, M, dim, lw.ln1_w, lw.ln1_b, ws.X, nullptr);
+      if ((rc = gemmf32::launch<gemmf32::kActGelu>(ws.X, dim, M, lw.wi, dim, I, lw.bi, nullptr, hbuf, I, st))) return rc;
+      if ((rc = gemmf32::launch<gemmf32::kActNone>(hbuf, I, M, lw.wo2, I, dim, lw.bo2, ws.X, ws.Y, dim, st))) return rc;
+      layernorm_kernel<<<wb_rows, 256, 0, st>>>(ws.Y, M, dim, lw.ln2_w, lw.ln2_b, ws.X, nullptr);
+    } else {
+      const uint8_t* b = pk + pl.layer_stride * li;
+      __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws.QKV);
+      __nv_bfloat16* ctx = reinterpret_cast<__nv_bfloat16*>(ws.CTX);
+      __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws.H);
+      if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wq, dim, lw.bq, qkv, 3 * dim, 0, nullptr, nullptr, sm_count, st))) return rc;
+      if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wk, dim, lw.bk, qkv, 3 * dim, dim, nullptr, nullptr, sm_count, st))) return rc;
+      if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wv, dim, lw.bv, qkv, 3 * dim, 2 * dim, nullptr, nullptr, sm_count, st))) return rc;
+      if ((rc = run_attention<__nv_bfloat16>(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ctx, dim, batch, heads, L, L, dh, st))) return rc;
+      if ((rc = tc_gemm<gemmtc::kEpiResidF32>(ctx, M, dim, b + pl.wo, dim, lw.bo, nullptr, dim, 0, ws.Y, ws.X, sm_count, st))) return rc;
+      layernorm_kernel<<<wb_rows, 256, 0, st>>>(ws.Y, M, dim, lw.ln1_w, lw.ln1_b, ws.X, Xb);
+      if ((rc = tc_gemm<gemmtc::kEpiGeluBf16>(Xb, M, dim, b + pl.wi, I, lw.bi, hbuf, I, 0, nullptr, nullptr, sm_count, st))) return rc;
+      if ((rc = tc_gemm<gemmtc::kEpiResidF32>(hbuf, M, I, b + pl.wo2, dim, lw.bo2, nullptr, dim, 0, ws.Y, ws.X, sm_count, st))) return rc;
+      layernorm_kernel<<<wb_rows, 256, 0, st>>>(ws.Y, M, dim, lw.ln2_w, lw.ln2_b, ws.X, Xb);
+    }
+    ERN_CUDA(cudaGetLastError());
+  }
+
+  // ---- normalise, seq_text_mean, cross attention (first P text positions -> P patches) ------------------------------
+  const int dd = dim * dim;
+  if (f32) {
+    float* img = reinterpret_cast<float*>(ws.img);
+    float* txt = reinterpret_cast<float*>(ws.txt);
+    float* mq = reinterpret_cast<float*>(ws.mq);
+    float* mkv = reinterpret_cast<float*>(ws.mkv);
+    float* mctx = reinterpret_cast<float*>(ws.mctx);
+    post_kernel<float><<<static_cast<unsigned>(batch), 256, 0, st>>>(ws.X, P, T, dim, img, txt, out_seq_mean);
+    if ((rc = gemmf32::launch<gemmf32::kActNone>(txt, dim, MP, w->mha_in_w, dim, dim, w->mha_in_b, nullptr, mq, dim, st))) return rc;
+    if ((rc = gemmf32::launch<gemmf32::kActNone>(img, dim, MP, w->mha_in_w + dd, dim, 2 * dim, w->mha_in_b + dim, nullptr, mkv, 2 * dim, st))) return rc;
+    if ((rc = run_attention<float>(mq, dim, mkv, 2 * dim, mkv + dim, 2 * dim, mctx, dim, batch, heads, P, P, dh, st))) return rc;
+    if ((rc = gemmf32::launch<gemmf32::kActNone>(mctx, dim, MP, w->mha_out_w, dim, dim, w->mha_out_b, nullptr, out_cross, dim, st))) return rc;
+  } else {
+    __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(ws.img);
+    __nv_bfloat16* txt = reinterpret_cast<__nv_bfloat16*>(ws.txt);
+    __nv_bfloat16* mq = reinterpret_cast<__nv_bfloat16*>(ws.mq);
+    __nv_bfloat16* mkv = reinterpret_cast<__nv_bfloat16*>(ws.mkv);
+    __nv_bfloat16* mctx = reinterpret_cast<__nv_bfloat16*>(ws.mctx);
+    post_kernel<__nv_bfloat16><<<static_cast<unsigned>(batch), 256, 0, st>>>(ws.X, P, T, dim, img, txt, out_seq_mean);
+    const uint8_t* win = pk + pl.mha_in;
+    if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(txt, MP, dim, win, dim, w->mha_in_b, mq, dim, 0, nullptr, nullptr, sm_count, st))) return rc;
+    if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(img, MP, dim, win + static_cast<size_t>(dd) * 2, 2 * dim, w->mha_in_b + dim, mkv, 2 * dim, 0, nullptr, nullptr, sm_count, st))) return rc;
+    if ((rc = run_attention<__nv_bfloat16>(mq, dim, mkv, 2 * dim, mkv + dim, 2 * dim, mctx, dim, batch, heads, P, P, dh, st))) return rc;
+    if ((rc = tc_gemm<gemmtc::kEpiResidF32>(mctx, MP, dim, pk + pl.mha_out, dim, w->mha_out_b, nullptr, dim, 0, out_cross, nullptr, sm_count, st))) return rc;
+  }
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
+}  // namespace dvr
+}  // namespace ern

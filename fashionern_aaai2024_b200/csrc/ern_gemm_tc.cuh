@@ -15,6 +15,9 @@ enum Epilogue {
   kEpiGate = 1,       // partial[r, tile]  = sum_n relu(acc + bias[n]) * wg[n]
   kEpiSrGlobal = 2,   // out_f32[r, n]     = tanh(scale[n] * (acc + bias[n]) + shift[n]) * wg[n]
   kEpiSrLocal = 3,    // partial[r, tile]  = sum_n tanh(scale[r % P] * (acc + bias[n]) + shift[r % P]) * cvec[r / P, n]
+  kEpiBiasBf16 = 4,   // out_bf16[r, col0 + n] = bf16(acc + bias[n])
+  kEpiGeluBf16 = 5,   // out_bf16[r, col0 + n] = bf16(gelu_erf(acc + bias[n]))
+  kEpiResidF32 = 6,   // out_f32[r, n] = acc + bias[n] + (residual ? residual[r, n] : 0)
 };
 
 constexpr int kBlockM = 128;
@@ -41,6 +44,7 @@ struct Params {
   const float* shift;
   const float* cvec;    // [M / P, N]         kEpiSrLocal
   int patches;          // P
+  const float* residual;  // [M, ldo] fp32     kEpiResidF32 (nullable)
 };
 
 struct Barriers {
@@ -224,12 +228,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               dst[j4] = make_float4(o[0], o[1], o[2], o[3]);
             }
           }
+        } else if (kEpi == kEpiResidF32) {
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + row * p.ldo + n0 + c * 32);
+            const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + row * p.ldo + n0 + c * 32) : nullptr;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 r4 = res ? res[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const int j = c * 32 + j4 * 4;
+              dst[j4] = make_float4(__uint_as_float(cur[j4 * 4 + 0]) + sbias[j + 0] + r4.x,
+                                    __uint_as_float(cur[j4 * 4 + 1]) + sbias[j + 1] + r4.y,
+                                    __uint_as_float(cur[j4 * 4 + 2]) + sbias[j + 2] + r4.z,
+                                    __uint_as_float(cur[j4 * 4 + 3]) + sbias[j + 3] + r4.w);
+            }
+          }
         } else {
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = fmaxf(__uint_as_float(cur[2 * j]) + sbias[c * 32 + 2 * j], 0.f);
-            const float b = fmaxf(__uint_as_float(cur[2 * j + 1]) + sbias[c * 32 + 2 * j + 1], 0.f);
+            float a = __uint_as_float(cur[2 * j]) + sbias[c * 32 + 2 * j];
+            float b = __uint_as_float(cur[2 * j + 1]) + sbias[c * 32 + 2 * j + 1];
+            if (kEpi == kEpiStoreRelu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            } else if (kEpi == kEpiGeluBf16) {
+              a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
+              b = 0.5f * b * (1.0f + erff(b * 0.70710678118654752f));
+            }
             packed[j] = pack_bf16x2(a, b);
           }
           if (row_ok) {

@@ -55,6 +55,14 @@ int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, con
                  cudaStream_t st);
 }
 
+namespace dvr {
+size_t packed_bytes(int dim, int inter, int n_layers);
+int pack(const ern_dvr_weights* w, int dim, void* packed, cudaStream_t st);
+size_t workspace_bytes(int64_t batch, int P, int T, int dim, int inter, int mode);
+int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode, const float* patches,
+           const float* tokens, int64_t batch, float* out_cross, float* out_seq_mean, void* workspace, int sm_count,
+           cudaStream_t st);
+}
 namespace visualsr {
 size_t packed_bytes(int dim);
 int pack(const ern_visualsr_weights* w, int dim, void* packed, cudaStream_t st);

@@ -77,6 +77,61 @@ def visualsr_state(seed: int, dim: int, patches: int = PATCHES) -> Dict[str, tor
     return sd
 
 
+BERT_LAYERS = 2            # models/fusion_model.py:14  (PlusModel(..., layers=2))
+BERT_INTERMEDIATE = 3072   # BertConfig default intermediate_size (models/fusion_model.py:162-170 does not set it)
+BERT_PREFIX = "transformer_layer.bert_encoder.bert_model."
+
+
+def dvr_state(seed: int, dim: int) -> Dict[str, torch.Tensor]:
+    """State dict of the transformer / cross-attention part of one ``DVR_module(dim)`` with the reference's key
+    names (models/fusion_model.py:8-24,157-216: HF ``BertModel`` without word embeddings, ``cls_token``,
+    ``nn.MultiheadAttention`` ``MR_component``).  Values are drawn from an explicit generator at BERT-like scales
+    (weights N(0, 0.02^2) scaled up a little so that attention is not uniform, LayerNorm affine near identity)."""
+    g = _gen(seed)
+
+    def normal(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    sd: Dict[str, torch.Tensor] = {}
+    sd["transformer_layer.cls_token"] = normal(1, 1, dim, std=0.5)
+    e = BERT_PREFIX + "embeddings."
+    sd[e + "position_embeddings.weight"] = normal(512, dim, std=0.1)
+    sd[e + "token_type_embeddings.weight"] = normal(2, dim, std=0.1)
+    sd[e + "LayerNorm.weight"] = 1.0 + normal(dim, std=0.1)
+    sd[e + "LayerNorm.bias"] = normal(dim, std=0.1)
+    for l in range(BERT_LAYERS):
+        p = f"{BERT_PREFIX}encoder.layer.{l}."
+        for nm in ("query", "key", "value"):
+            sd[p + f"attention.self.{nm}.weight"] = normal(dim, dim, std=0.06)
+            sd[p + f"attention.self.{nm}.bias"] = normal(dim, std=0.05)
+        sd[p + "attention.output.dense.weight"] = normal(dim, dim, std=0.04)
+        sd[p + "attention.output.dense.bias"] = normal(dim, std=0.05)
+        sd[p + "attention.output.LayerNorm.weight"] = 1.0 + normal(dim, std=0.1)
+        sd[p + "attention.output.LayerNorm.bias"] = normal(dim, std=0.1)
+        sd[p + "intermediate.dense.weight"] = normal(BERT_INTERMEDIATE, dim, std=0.04)
+        sd[p + "intermediate.dense.bias"] = normal(BERT_INTERMEDIATE, std=0.05)
+        sd[p + "output.dense.weight"] = normal(dim, BERT_INTERMEDIATE, std=0.03)
+        sd[p + "output.dense.bias"] = normal(dim, std=0.05)
+        sd[p + "output.LayerNorm.weight"] = 1.0 + normal(dim, std=0.1)
+        sd[p + "output.LayerNorm.bias"] = normal(dim, std=0.1)
+    sd[BERT_PREFIX + "pooler.dense.weight"] = normal(dim, dim)
+    sd[BERT_PREFIX + "pooler.dense.bias"] = normal(dim)
+    sd["MR_component.in_proj_weight"] = normal(3 * dim, dim, std=0.08)
+    sd["MR_component.in_proj_bias"] = normal(3 * dim, std=0.05)
+    sd["MR_component.out_proj.weight"] = normal(dim, dim, std=0.05)
+    sd["MR_component.out_proj.bias"] = normal(dim, std=0.05)
+    return sd
+
+
+def dvr_full_state(seed: int, dim: int) -> Dict[str, torch.Tensor]:
+    """Complete ``DVR_module`` state dict: transformer + MR_component + SR_module + the three fusion heads."""
+    sd = dvr_state(seed, dim)
+    sd.update({f"SR_module.{k}": v for k, v in visualsr_state(seed + 1, dim).items()})
+    for i, name in enumerate(("combiner_global", "combiner_local", "combiner")):
+        sd.update({f"{name}.{k}": v for k, v in combiner_state(seed + 2 + i, dim).items()})
+    return sd
+
+
 def features(seed: int, rows: int, dim: int, unit: bool = False) -> torch.Tensor:
     x = torch.randn(rows, dim, generator=_gen(seed))
     if unit:

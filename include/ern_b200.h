@@ -136,6 +136,48 @@ ERN_API int ern_visualsr_forward(const ern_visualsr_weights* w, int dim, int pat
                          size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Query-side encoder of DVR_module in eval mode (models/fusion_model.py:26-49):
+ * PlusModel = HF BERT encoder over [CLS] + P patch + T token embeddings (:187-216), F.normalize of the
+ * patch/token states (:38-41), nn.MultiheadAttention cross attention of which only the first P query
+ * positions are used (:44-47), mean of the normalised token states (:49).
+ *   patches [B,P,D], tokens [B,T,D] fp32  ->  out_cross [B,P,D] (input of SR_module),
+ *                                            out_seq_mean [B,D] (text input of combiner_local)
+ * Linear weights are torch's fp32 [out,in]; ERN_MODE_BF16 needs dim % 128 == 0, intermediate % 128 == 0
+ * and packed weights (ern_dvr_pack).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ern_bert_layer_weights {
+  const float *wq, *bq, *wk, *bk, *wv, *bv; /* attention.self.{query,key,value}          */
+  const float *wo, *bo, *ln1_w, *ln1_b;     /* attention.output.{dense,LayerNorm}         */
+  const float *wi, *bi;                     /* intermediate.dense [I, D]                  */
+  const float *wo2, *bo2, *ln2_w, *ln2_b;   /* output.{dense [D, I],LayerNorm}            */
+} ern_bert_layer_weights;
+
+#define ERN_MAX_BERT_LAYERS 4
+typedef struct ern_dvr_weights {
+  const float* cls_token; /* transformer_layer.cls_token [D]                                    */
+  const float* pos_emb;   /* embeddings.position_embeddings.weight [>= 1+P+T, D]                */
+  const float* type_emb;  /* embeddings.token_type_embeddings.weight [2, D]                     */
+  const float* emb_ln_w;  /* embeddings.LayerNorm                                               */
+  const float* emb_ln_b;
+  int n_layers;
+  int intermediate;
+  ern_bert_layer_weights layers[ERN_MAX_BERT_LAYERS];
+  const float* mha_in_w;  /* MR_component.in_proj_weight [3D, D]                                */
+  const float* mha_in_b;  /* MR_component.in_proj_bias   [3D]                                   */
+  const float* mha_out_w; /* MR_component.out_proj.weight [D, D]                                */
+  const float* mha_out_b;
+  const void* packed_bf16;
+} ern_dvr_weights;
+
+ERN_API size_t ern_dvr_packed_bytes(int dim, int intermediate, int n_layers);
+ERN_API int ern_dvr_pack(const ern_dvr_weights* w, int dim, void* packed_dev, void* stream);
+ERN_API size_t ern_dvr_workspace_bytes(int64_t batch, int patches, int tokens, int dim, int intermediate, int mode);
+ERN_API int ern_dvr_encode(const ern_dvr_weights* w, int dim, int heads, int patches, int tokens, int mode,
+                   const float* patches_dev, const float* tokens_dev, int64_t batch,
+                   float* out_cross_dev, float* out_seq_mean_dev, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Similarity + streaming per-query top-k over one gallery shard.
  * Replaces `distances = 1 - predicted_features @ index_features.T;
  *           sorted_indices = torch.argsort(distances, dim=-1)` (run/test/test_fiq.py:49-50 and twins)

@@ -69,6 +69,59 @@ def visual_sr_forward(sd: Dict[str, torch.Tensor], local_feature: torch.Tensor, 
     return new_global / norm
 
 
+def _layer_norm(x, w, b, eps=1e-12):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def dvr_forward(sd: Dict[str, torch.Tensor], ref_patch_features: torch.Tensor, text_seq_features: torch.Tensor,
+                ref_global_feats: torch.Tensor, text_global_feats: torch.Tensor, heads: int = 8,
+                return_hidden: bool = False):
+    """``DVR_module.forward`` in eval mode -- models/fusion_model.py:26-55, with ``PlusModel.forward`` (:187-216: HF
+    BERT encoder over [CLS] + 13 patches + 77 tokens fed through ``inputs_embeds``) and the ``nn.MultiheadAttention``
+    cross attention (:44-46) written out explicitly.  Dropouts are identities in eval."""
+    B, P, D = ref_patch_features.shape
+    T = text_seq_features.shape[1]
+    L = 1 + P + T
+    pre = "transformer_layer.bert_encoder.bert_model."
+    x = torch.cat((sd["transformer_layer.cls_token"].expand(B, -1, -1), ref_patch_features.float(),
+                   text_seq_features.float()), dim=1)                                              # :199-201
+    tt = torch.cat((torch.zeros(P + 1, dtype=torch.long), torch.ones(T, dtype=torch.long)))        # :202-203
+    x = x + sd[pre + "embeddings.token_type_embeddings.weight"][tt] + sd[pre + "embeddings.position_embeddings.weight"][:L]
+    x = _layer_norm(x, sd[pre + "embeddings.LayerNorm.weight"], sd[pre + "embeddings.LayerNorm.bias"])
+    dh = D // heads
+    layer = 0
+    while (pre + f"encoder.layer.{layer}.attention.self.query.weight") in sd:
+        p = pre + f"encoder.layer.{layer}."
+        q = F.linear(x, sd[p + "attention.self.query.weight"], sd[p + "attention.self.query.bias"]).view(B, L, heads, dh).transpose(1, 2)
+        k = F.linear(x, sd[p + "attention.self.key.weight"], sd[p + "attention.self.key.bias"]).view(B, L, heads, dh).transpose(1, 2)
+        v = F.linear(x, sd[p + "attention.self.value.weight"], sd[p + "attention.self.value.bias"]).view(B, L, heads, dh).transpose(1, 2)
+        a = torch.softmax(q @ k.transpose(-1, -2) / (dh ** 0.5), dim=-1)                          # attention_mask is all ones (:204)
+        ctx = (a @ v).transpose(1, 2).reshape(B, L, D)
+        x = _layer_norm(F.linear(ctx, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"]) + x,
+                        sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"])
+        h = F.gelu(F.linear(x, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
+        x = _layer_norm(F.linear(h, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"]) + x,
+                        sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"])
+        layer += 1
+    hidden = x                                                                                     # last_hidden_state (:213)
+    image_norm = F.normalize(hidden[:, 1:P + 1], dim=2)                                            # :38-41
+    text_norm = F.normalize(hidden[:, P + 1:], dim=2)
+    w, bqkv = sd["MR_component.in_proj_weight"], sd["MR_component.in_proj_bias"]
+    # only the first P query positions of the cross attention are used downstream (:47)
+    q = F.linear(text_norm[:, :P], w[:D], bqkv[:D]).view(B, P, heads, dh).transpose(1, 2)
+    k = F.linear(image_norm, w[D:2 * D], bqkv[D:2 * D]).view(B, P, heads, dh).transpose(1, 2)
+    v = F.linear(image_norm, w[2 * D:], bqkv[2 * D:]).view(B, P, heads, dh).transpose(1, 2)
+    a = torch.softmax(q @ k.transpose(-1, -2) / (dh ** 0.5), dim=-1)
+    cross = F.linear((a @ v).transpose(1, 2).reshape(B, P, D), sd["MR_component.out_proj.weight"], sd["MR_component.out_proj.bias"])
+    sub = lambda prefix: {kk[len(prefix):]: vv for kk, vv in sd.items() if kk.startswith(prefix)}  # noqa: E731
+    patch_vision_mean = visual_sr_forward(sub("SR_module."), cross)                               # :48
+    seq_text_mean = text_norm.mean(dim=1)                                                          # :49
+    global_feats = combiner_forward(sub("combiner_global."), ref_global_feats, text_global_feats)  # :52
+    local_feats = combiner_forward(sub("combiner_local."), patch_vision_mean, seq_text_mean)      # :53
+    fusion = combiner_forward(sub("combiner."), global_feats, local_feats)                         # :54
+    return (fusion, hidden) if return_hidden else fusion
+
+
 def gallery_normalize(index_features: torch.Tensor) -> torch.Tensor:
     """``F.normalize(index_features, dim=-1).float()`` -- run/test/test_fiq.py:45 (and twins)."""
     return F.normalize(index_features, dim=-1).float()

@@ -233,6 +233,29 @@ def make_visualsr_golden(dim, rows, seed):
     return {"dim": dim, "rows": rows, "seed": seed}
 
 
+def make_dvr_golden(dim, rows, seed):
+    """Reference ``DVR_module`` (BERT + MHA + VisualSR + 3 heads) verbatim vs the explicit restatement."""
+    ref.install()
+    from models.fusion_model import DVR_module
+    sd = syn.dvr_full_state(seed, dim)
+    m = DVR_module(feature_dim=dim, device="cpu")
+    missing = m.load_state_dict(sd, strict=True)
+    m = m.eval().float()
+    patches = syn.patch_features(seed + 10, rows, dim)
+    tokens = syn.token_features(seed + 11, rows, dim)
+    ref_g, txt_g = syn.features(seed + 12, rows, dim), syn.features(seed + 13, rows, dim)
+    with torch.no_grad():
+        out = m(patches, tokens, ref_g, txt_g)
+        _, hidden, _ = m.transformer_layer(patches, tokens)
+    mine, hid = orc.dvr_forward(sd, patches, tokens, ref_g, txt_g, return_hidden=True)
+    err_h, err_o = float((hid - hidden).abs().max()), float((mine - out).abs().max())
+    assert err_h < 2e-5 and err_o < 2e-6, (err_h, err_o)
+    np.savez(os.path.join(GOLDEN, f"dvr{dim}.npz"), out=out.numpy(), hidden_cls=hidden[:, 0].numpy(),
+             hidden_last=hidden[:, -1].numpy(),
+             meta=np.array(json.dumps({"dim": dim, "rows": rows, "seed": seed, "err_hidden": err_h, "err_out": err_o})))
+    return {"dim": dim, "rows": rows, "seed": seed, "err_hidden_restatement": err_h, "err_out_restatement": err_o}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-full", action="store_true")
@@ -243,10 +266,12 @@ def main():
     torch.set_num_threads(os.cpu_count())
     report = {"torch": torch.__version__, "numpy": np.__version__, "cases": {}, "full": {}}
     report["visualsr"] = [make_visualsr_golden(640, 40, 300), make_visualsr_golden(512, 40, 400)]
+    report["dvr"] = [make_dvr_golden(640, 6, 500), make_dvr_golden(512, 6, 600)]
     if args.only_visualsr:
         with open(os.path.join(GOLDEN, "pin_report.json")) as f:
             old = json.load(f)
         old["visualsr"] = report["visualsr"]
+        old["dvr"] = report["dvr"]
         with open(os.path.join(GOLDEN, "pin_report.json"), "w") as f:
             json.dump(old, f, indent=1)
         return
@@ -254,6 +279,7 @@ def main():
         with open(os.path.join(GOLDEN, "pin_report.json")) as f:
             old = json.load(f)
         old["visualsr"] = report["visualsr"]
+        old["dvr"] = report["dvr"]
         report = old
         report["full"] = {}
     else:

@@ -88,6 +88,8 @@ def test_accelerate_ern_swaps_reference_modules_and_keeps_weights():
     before = {k: v.clone() for k, v in model.state_dict().items()}
     model = accelerate_ern(model, mode="fp32")
     assert isinstance(model.Combiner_module, CombinerSimple) and isinstance(model.DVR.combiner, CombinerSimple)
+    from fashionern_aaai2024_b200 import DVR_module
+    assert isinstance(model.DVR, DVR_module)
     assert isinstance(model.SR_module, VisualSR) and isinstance(model.DVR.SR_module, VisualSR)
     after = model.state_dict()
     assert set(after.keys()) == set(before.keys())             # checkpoints stay loadable both ways

@@ -102,3 +102,16 @@ def test_visualsr_restatement_matches_reference(dim):
     assert torch.allclose(out, torch.from_numpy(z["out"]), atol=2e-7, rtol=0)
     n = out.norm(dim=-1)
     assert torch.allclose(n, torch.ones_like(n), atol=1e-5)
+
+
+@pytest.mark.parametrize("dim", [640, 512])
+def test_dvr_restatement_matches_reference(dim):
+    # reference DVR_module (HF BERT + nn.MultiheadAttention + VisualSR + 3 heads) vs the explicit restatement
+    z, meta = load_golden(f"dvr{dim}")
+    sd = syn.dvr_full_state(meta["seed"], dim)
+    s, rows = meta["seed"], meta["rows"]
+    out, hidden = orc.dvr_forward(sd, syn.patch_features(s + 10, rows, dim), syn.token_features(s + 11, rows, dim),
+                                  syn.features(s + 12, rows, dim), syn.features(s + 13, rows, dim), return_hidden=True)
+    assert float((out - torch.from_numpy(z["out"])).abs().max()) < 2e-6
+    assert float((hidden[:, 0] - torch.from_numpy(z["hidden_cls"])).abs().max()) < 2e-5
+    assert float((hidden[:, -1] - torch.from_numpy(z["hidden_last"])).abs().max()) < 2e-5
