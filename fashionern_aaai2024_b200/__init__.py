@@ -15,6 +15,7 @@ from ._lib import ErnError, MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARIT
 from .combiner import CombinerSimple, accelerate_ern  # noqa: F401
 from .visual_sr import VisualSR  # noqa: F401
 from .dvr import DVR_module  # noqa: F401
+from .model import ERN  # noqa: F401
 from . import ops, sharded, store  # noqa: F401
 from .metrics import (compute_200k_val_metrics, compute_cirr_val_metrics, compute_fiq_val_metrics,  # noqa: F401
                       compute_shoes_val_metrics, compute_val_metrics, score_topk_recall, set_precision,

@@ -132,6 +132,14 @@ def dvr_full_state(seed: int, dim: int) -> Dict[str, torch.Tensor]:
     return sd
 
 
+def ern_full_state(seed: int, dim: int) -> Dict[str, torch.Tensor]:
+    """Complete ``ERN`` state dict (models/model.py:16-20) minus the CLIP backbone: DVR.*, SR_module.*, Combiner_module.*"""
+    sd = {f"DVR.{k}": v for k, v in dvr_full_state(seed, dim).items()}
+    sd.update({f"SR_module.{k}": v for k, v in visualsr_state(seed + 20, dim).items()})
+    sd.update({f"Combiner_module.{k}": v for k, v in combiner_state(seed + 21, dim).items()})
+    return sd
+
+
 def features(seed: int, rows: int, dim: int, unit: bool = False) -> torch.Tensor:
     x = torch.randn(rows, dim, generator=_gen(seed))
     if unit:

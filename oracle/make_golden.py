@@ -256,6 +256,42 @@ def make_dvr_golden(dim, rows, seed):
     return {"dim": dim, "rows": rows, "seed": seed, "err_hidden_restatement": err_h, "err_out_restatement": err_o}
 
 
+def make_full_model_golden(name, kind, dim, q, n, seed):
+    """The WHOLE reference model (BERT, MHA, VisualSR, four heads) with synthetic weights through the unmodified
+    ``compute_*_val_metrics``: pins the fully accelerated ERN (DVR + SR + heads on the B200 path) end to end."""
+    inp = case_inputs(kind, dim, q, n, seed)
+    ref.install()
+    from models.model import ERN
+    model = ERN(ref.FakeClip(None, None), dim, "cpu")
+    model.load_state_dict(syn.ern_full_state(seed + 50, dim))
+    model = model.eval().float()
+    clip = ref.FakeClip(inp["text_global"], inp["text_seq"])
+    ref_idx, tgt = inp["ref_idx"].clone(), inp["rand_tgt"].clone()
+    same = tgt == ref_idx
+    tgt[same] = (tgt[same] + 1) % n
+    mem = cirr_members(seed + 7, q, n, ref_idx, tgt) if kind == "cirr" else None
+    _, pred1, _, sorted1, *_ = run_reference(kind, dim, inp, ref_idx, tgt, mem, model, clip)
+    ranks = syn.planted_ranks(seed + 5, q, max_rank=min(100, n - 2))
+    planted = torch.empty(q, dtype=torch.long)
+    for i in range(q):
+        row = sorted1[i]
+        if kind == "cirr":
+            row = row[row != ref_idx[i]]
+        planted[i] = row[int(ranks[i])]
+    mem2 = cirr_members(seed + 8, q, n, ref_idx, planted) if kind == "cirr" else None
+    res, pred, rec, sorted2, ref_names, tgt_names, members = run_reference(kind, dim, inp, ref_idx, planted, mem2, model, clip)
+    gallery = rec.index_out
+    d_ref = torch.gather(orc.distances(pred, gallery), 1, sorted2[:, :TOPC])
+    np.savez(os.path.join(GOLDEN, f"{name}.npz"), pred=pred.numpy(), gallery_head=gallery[:16].numpy(),
+             ref_top=sorted2[:, :TOPC].numpy().astype(np.int32), ref_dist=d_ref.numpy(),
+             ref_idx=ref_idx.numpy().astype(np.int32), tgt_idx=planted.numpy().astype(np.int32),
+             members=np.array(mem2 if mem2 is not None else [], dtype=np.int32), recall=np.array(res, dtype=np.float64),
+             meta=np.array(json.dumps({"kind": kind, "dim": dim, "q": q, "n": n, "seed": seed, "recall": list(map(float, res)),
+                                       "digest_index_features": syn.tensor_digest(inp["index_features"]),
+                                       "digest_index_local": syn.tensor_digest(inp["index_local"])})))
+    return {"kind": kind, "dim": dim, "q": q, "n": n, "seed": seed, "recall": [float(x) for x in res]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-full", action="store_true")
@@ -267,11 +303,14 @@ def main():
     report = {"torch": torch.__version__, "numpy": np.__version__, "cases": {}, "full": {}}
     report["visualsr"] = [make_visualsr_golden(640, 40, 300), make_visualsr_golden(512, 40, 400)]
     report["dvr"] = [make_dvr_golden(640, 6, 500), make_dvr_golden(512, 6, 600)]
+    report["full_model"] = [make_full_model_golden("ernfull_fiq640", "fiq", 640, 40, 160, 1300),
+                            make_full_model_golden("ernfull_cirr512", "cirr", 512, 40, 160, 1310)]
     if args.only_visualsr:
         with open(os.path.join(GOLDEN, "pin_report.json")) as f:
             old = json.load(f)
         old["visualsr"] = report["visualsr"]
         old["dvr"] = report["dvr"]
+        old["full_model"] = report["full_model"]
         with open(os.path.join(GOLDEN, "pin_report.json"), "w") as f:
             json.dump(old, f, indent=1)
         return
@@ -280,6 +319,7 @@ def main():
             old = json.load(f)
         old["visualsr"] = report["visualsr"]
         old["dvr"] = report["dvr"]
+        old["full_model"] = report["full_model"]
         report = old
         report["full"] = {}
     else:

@@ -99,3 +99,16 @@ class StandInERN(torch.nn.Module):
         if mode == "index":
             return self.Combiner_module(tar_feats, self.sr_out)
         raise ValueError(mode)
+
+
+class SeededClip:
+    """encode_text stand-in serving seeded text features by query index (same as oracle/ref_harness.FakeClip)."""
+
+    def __init__(self, text_global, text_seq):
+        self.text_global, self.text_seq = text_global, text_seq
+
+    def encode_text(self, tokens, mode="global", visual_emb=None):
+        idx = tokens[:, 0].long().to(self.text_global.device)
+        if mode == "seq":
+            return self.text_seq[idx]
+        return self.text_global[idx], None

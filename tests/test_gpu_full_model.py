@@ -1,0 +1,64 @@
+"""GPU: the fully accelerated ERN (DVR encoder + VisualSR + four fusion heads + scoring tail, nothing from the
+reference on the path) against recall tuples the UNMODIFIED reference model produced with the same weights."""
+import numpy as np
+import pytest
+import torch
+
+import fashionern_aaai2024_b200 as ern
+from fashionern_aaai2024_b200 import metrics, synthetic as syn
+from helpers import FakeRelative, SeededClip, fake_tokenizer_factory, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def build(name, dev, mode):
+    z, meta = load_golden(name)
+    kind, dim, q, n, seed = meta["kind"], meta["dim"], meta["q"], meta["n"], meta["seed"]
+    index_features, index_local = syn.features(seed + 1, n, dim), syn.patch_features(seed + 2, n, dim)
+    assert syn.tensor_digest(index_features) == meta["digest_index_features"]
+    text_global, text_seq = syn.features(seed + 3, q, dim).to(dev), syn.token_features(seed + 4, q, dim).to(dev)
+    names = syn.unique_names(n, "dev-{}-img") if kind == "cirr" else syn.unique_names(n)
+    model = ern.ERN(SeededClip(text_global, text_seq), dim, dev, mode=mode)
+    model.load_state_dict(syn.ern_full_state(seed + 50, dim))
+    model = model.eval()
+    ref_names = [names[i] for i in z["ref_idx"]]
+    tgt_names = [names[i] for i in z["tgt_idx"]]
+    members = [[names[m] for m in row] for row in z["members"]] if kind == "cirr" else None
+    ds = FakeRelative(kind, ref_names, tgt_names, index_local[torch.from_numpy(z["ref_idx"]).long()], members)
+    return z, meta, ds, model.DVR, model, index_features.to(dev), index_local.to(dev), names
+
+
+@pytest.fixture(autouse=True)
+def _tok():
+    metrics.set_tokenizer_factory(fake_tokenizer_factory)
+    yield
+    metrics.set_tokenizer_factory(None)
+
+
+@pytest.mark.parametrize("name,fn", [("ernfull_fiq640", metrics.compute_fiq_val_metrics),
+                                     ("ernfull_cirr512", metrics.compute_cirr_val_metrics)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_whole_model_reproduces_reference_recall(cuda_device, name, fn, mode):
+    z, meta, ds, _, model, feats, local, names = build(name, cuda_device, mode)
+    clip = model.text_clip  # unused handle; the metric function receives the CLIP stand-in explicitly
+    out = fn(ds, object.__getattribute__(clip, "_clip"), feats, local, names, model, cuda_device, meta["dim"], 16, 0,
+             "RN50x4", precision=mode)
+    ref = z["recall"].tolist()
+    q, d = meta["q"], z["ref_dist"]
+    tol = 2e-4 if mode == "fp32" else 6e-3        # a query may cross a K boundary only inside such a near-tie
+    ks = (10, 50) if meta["kind"] == "fiq" else (1, 2, 3, 1, 5, 10, 50)
+    for i, (got, want, k) in enumerate(zip(out, ref, ks)):
+        if meta["kind"] == "cirr" and i < 3:
+            near = q if mode == "bf16" else 2
+        else:
+            near = int(np.sum(np.abs(d[:, min(k, d.shape[1] - 1)] - d[:, k - 1]) < tol))
+        assert abs(got - want) <= 100.0 * near / q + 1e-9, (k, got, want, near)
+
+
+def test_query_features_match_reference(cuda_device):
+    z, meta, ds, dvr, model, feats, local, names = build("ernfull_fiq640", cuda_device, "fp32")
+    pred, _ = metrics.generate_fiq_val_predictions(object.__getattribute__(model.text_clip, "_clip"), ds, model, names,
+                                                   feats, cuda_device, 640, 16, 0, "RN50x4")
+    assert float((pred.cpu() - torch.from_numpy(z["pred"])).norm(dim=-1).max()) <= 2e-5
+    gal = metrics.prepare_gallery(feats, local, model, cuda_device)
+    assert float((gal[:16].cpu() - torch.from_numpy(z["gallery_head"])).norm(dim=-1).max()) <= 1e-5
