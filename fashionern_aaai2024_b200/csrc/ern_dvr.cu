@@ -93,8 +93,10 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // softmax(Q K^T * scale) V for one (batch element, head); sequences are short (<= 91), everything lives in smem
+constexpr int kAttnThreads = 512;   // 16 warps on the one block that fits per SM: hides the smem/FMA latencies
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ K, int64_t ldk, const T* __restrict__ V,
                  int64_t ldv, T* __restrict__ O, int64_t ldo, int Lq, int Lk, int dh, float scale) {
   extern __shared__ float sm[];
@@ -107,25 +109,60 @@ attention_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ K, 
   float* S = Vs + Lk * pitch;   // [Lq][Lk + 1]
   const int sp = Lk + 1;
   const int tid = threadIdx.x;
-  for (int e = tid; e < Lq * dh; e += 256) {
-    const int i = e / dh, d = e % dh;
-    Qs[i * pitch + d] = to_f(Q[(b * Lq + i) * ldq + h * dh + d]);
-  }
-  for (int e = tid; e < Lk * dh; e += 256) {
-    const int j = e / dh, d = e % dh;
-    Ks[j * pitch + d] = to_f(K[(b * Lk + j) * ldk + h * dh + d]);
-    Vs[j * pitch + d] = to_f(V[(b * Lk + j) * ldv + h * dh + d]);
-  }
+  // head slices are contiguous (dh elements per row): 16-byte vector loads, converted to fp32 in shared memory
+  constexpr int kVec = 16 / sizeof(T);
+  const int vpr = dh / kVec;   // vectors per row (dh % kVec == 0 is checked by the launcher)
+  auto load_rows = [&](const T* src, int64_t ld, int rows, float* dst) {
+    for (int e = tid; e < rows * vpr; e += kAttnThreads) {
+      const int r = e / vpr, v = e - r * vpr;
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + (b * rows + r) * ld + h * dh + v * kVec);
+      const T* vals = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+      for (int u = 0; u < kVec; ++u) dst[r * pitch + v * kVec + u] = to_f(vals[u]);
+    }
+  };
+  load_rows(Q, ldq, Lq, Qs);
+  load_rows(K, ldk, Lk, Ks);
+  load_rows(V, ldv, Lk, Vs);
   __syncthreads();
-  for (int e = tid; e < Lq * Lk; e += 256) {
-    const int i = e / Lk, j = e % Lk;
-    float acc = 0.f;
-    for (int d = 0; d < dh; ++d) acc = fmaf(Qs[i * pitch + d], Ks[j * pitch + d], acc);
-    S[i * sp + j] = acc * scale;
+  // S = scale * Q K^T with 4 x 4 register tiles.  A thread's rows/columns are STRIDED (i = ib + nbi*ii, j = jb + nbj*jj)
+  // so that consecutive lanes read consecutive rows of K: pitch dh+1 is odd => conflict-free; Q reads broadcast.
+  {
+    const int nbi = (Lq + 3) >> 2, nbj = (Lk + 3) >> 2;
+    for (int blk = tid; blk < nbi * nbj; blk += kAttnThreads) {
+      const int ib = blk / nbj, jb = blk % nbj;
+      float acc[4][4] = {};
+      const float* qp[4];
+      const float* kp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        qp[u] = Qs + min(ib + nbi * u, Lq - 1) * pitch;
+        kp[u] = Ks + min(jb + nbj * u, Lk - 1) * pitch;
+      }
+      for (int d = 0; d < dh; ++d) {
+        float qv[4], kv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          qv[u] = qp[u][d];
+          kv[u] = kp[u][d];
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = fmaf(qv[ii], kv[jj], acc[ii][jj]);
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = ib + nbi * ii, j = jb + nbj * jj;
+          if (i < Lq && j < Lk) S[i * sp + j] = acc[ii][jj] * scale;
+        }
+    }
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  for (int i = warp; i < Lq; i += 8) {
+  for (int i = warp; i < Lq; i += kAttnThreads / 32) {
     float mx = -INFINITY;
     for (int j = lane; j < Lk; j += 32) mx = fmaxf(mx, S[i * sp + j]);
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -139,11 +176,40 @@ attention_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ K, 
     for (int j = lane; j < Lk; j += 32) S[i * sp + j] = S[i * sp + j] / sum;
   }
   __syncthreads();
-  for (int e = tid; e < Lq * dh; e += 256) {
-    const int i = e / dh, d = e % dh;
-    float acc = 0.f;
-    for (int j = 0; j < Lk; ++j) acc = fmaf(S[i * sp + j], Vs[j * pitch + d], acc);
-    O[(b * Lq + i) * ldo + h * dh + d] = from_f<T>(acc);
+  // O = P V with 4 x 4 register tiles: rows strided as above, columns d = db + nbd*dd (consecutive lanes ->
+  // consecutive d: conflict-free V reads; P reads broadcast)
+  {
+    const int nbi = (Lq + 3) >> 2, nbd = (dh + 3) >> 2;
+    for (int blk = tid; blk < nbi * nbd; blk += kAttnThreads) {
+      const int ib = blk / nbd, db = blk % nbd;
+      float acc[4][4] = {};
+      const float* pp[4];
+      int dcol[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pp[u] = S + min(ib + nbi * u, Lq - 1) * sp;
+        dcol[u] = min(db + nbd * u, dh - 1);
+      }
+      for (int j = 0; j < Lk; ++j) {
+        float pv[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pv[u] = pp[u][j];
+          vv[u] = Vs[j * pitch + dcol[u]];
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) acc[ii][dd] = fmaf(pv[ii], vv[dd], acc[ii][dd]);
+      }
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+          const int i = ib + nbi * ii, d = db + nbd * dd;
+          if (i < Lq && d < dh) O[(b * Lq + i) * ldo + h * dh + d] = from_f<T>(acc[ii][dd]);
+        }
+    }
   }
 }
 
@@ -276,6 +342,9 @@ size_t workspace_bytes(int64_t batch, int P, int T, int dim, int inter, int mode
 template <typename T>
 static int run_attention(const T* Q, int64_t ldq, const T* K, int64_t ldk, const T* V, int64_t ldv, T* O, int64_t ldo,
                          int64_t batch, int heads, int Lq, int Lk, int dh, cudaStream_t st) {
+  ERN_REQUIRE(dh % (16 / static_cast<int>(sizeof(T))) == 0 && (ldq * sizeof(T)) % 16 == 0 && (ldk * sizeof(T)) % 16 == 0 &&
+                  (ldv * sizeof(T)) % 16 == 0,
+              "attention: head size and row strides must allow 16-byte loads (dh = %d)", dh);
   const size_t smem = (static_cast<size_t>(Lq + 2 * Lk) * (dh + 1) + static_cast<size_t>(Lq) * (Lk + 1)) * 4;
   auto kern = attention_kernel<T>;
   static size_t configured[64] = {};
@@ -287,7 +356,7 @@ static int run_attention(const T* Q, int64_t ldq, const T* K, int64_t ldk, const
   }
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
-    kern<<<dim3(heads, static_cast<unsigned>(nb)), 256, smem, st>>>(Q + b0 * Lq * ldq, ldq, K + b0 * Lk * ldk, ldk,
+    kern<<<dim3(heads, static_cast<unsigned>(nb)), kAttnThreads, smem, st>>>(Q + b0 * Lq * ldq, ldq, K + b0 * Lk * ldk, ldk,
                                                                    V + b0 * Lk * ldv, ldv, O + b0 * Lq * ldo, ldo, Lq, Lk,
                                                                    dh, 1.0f / sqrtf(static_cast<float>(dh)));
   }

@@ -59,6 +59,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// erf-GELU for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 rounding of
+// the stored activation) -- ~4x fewer instructions than erff in an epilogue that otherwise paces the GEMM
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  const float erf_x = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_x);
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -252,8 +265,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             } else if (kEpi == kEpiGeluBf16) {
-              a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
-              b = 0.5f * b * (1.0f + erff(b * 0.70710678118654752f));
+              a = gelu_erf_fast(a);
+              b = gelu_erf_fast(b);
             }
             packed[j] = pack_bf16x2(a, b);
           }

@@ -47,6 +47,20 @@ def main():
                 flop = rows * 14 * 2.0 * dim * dim
                 out.append({"op": "VisualSR", "dim": dim, "rows": rows, "ms": ms, "tflops": flop / ms / 1e9,
                             "gbps_in": rows * 13 * dim * 4 / ms / 1e6})
+    for dim in (640, 512):
+        dvr = ern.DVR_module(dim)
+        dvr.load_state_dict(syn.dvr_full_state(3, dim))
+        dvr = dvr.to(dev).eval()
+        for rows in (32, 512, 4096):
+            pt, tk = torch.randn(rows, 13, dim, device=dev), torch.randn(rows, 77, dim, device=dev)
+            a, b = torch.randn(rows, dim, device=dev), torch.randn(rows, dim, device=dev)
+            with torch.no_grad():
+                ms_enc = timeit(lambda: dvr.encode(pt, tk), iters=5)
+                ms_all = timeit(lambda: dvr(pt, tk, a, b), iters=5)
+            L, I = 91, 3072
+            flop = rows * (2 * (L * (8.0 * dim * dim + 4.0 * dim * I) + 4.0 * L * L * dim) + 13 * 8.0 * dim * dim)
+            out.append({"op": "DVR.encode", "dim": dim, "rows": rows, "ms": ms_enc, "tflops": flop / ms_enc / 1e9,
+                        "queries_per_s": rows / ms_enc * 1e3, "ms_full_forward": ms_all})
     for o in out:
         print(json.dumps(o))
 
