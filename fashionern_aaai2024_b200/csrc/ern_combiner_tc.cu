@@ -60,10 +60,10 @@ int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, con
   // text projection -> raw[:, 0:4D], image projection -> raw[:, 4D:8D]  (text half first, fusion_model.py:90)
   p.bias = pv.bt;
   p.col0 = 0;
-  if ((rc = gemmtc::launch<kGemmBlockN, gemmtc::kEpiStoreRelu>(t_txt, t_wt, p, sm_count, st))) return rc;
+  if ((rc = gemmtc::launch<kGemmBlockN, gemmtc::kEpiStoreRelu, true>(t_txt, t_wt, p, sm_count, st))) return rc;
   p.bias = pv.bi;
   p.col0 = proj;
-  if ((rc = gemmtc::launch<kGemmBlockN, gemmtc::kEpiStoreRelu>(t_img, t_wi, p, sm_count, st))) return rc;
+  if ((rc = gemmtc::launch<kGemmBlockN, gemmtc::kEpiStoreRelu, true>(t_img, t_wi, p, sm_count, st))) return rc;
   // hidden layer + gate dot product
   gemmtc::Params g{};
   g.m = rows;
@@ -72,7 +72,7 @@ int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, con
   g.bias = pv.b1;
   g.wg = pv.w2;
   g.partial = partial;
-  if ((rc = gemmtc::launch<kGemmBlockN, gemmtc::kEpiGate>(t_raw, t_w1, g, sm_count, st))) return rc;
+  if ((rc = gemmtc::launch<kGemmBlockN, gemmtc::kEpiGate, true>(t_raw, t_w1, g, sm_count, st))) return rc;
   return launch_finalize(image, text, rows, dim, partial, n_tiles, pv.b2, out, out_bf16, ldb, gate, st);
 }
 

@@ -382,7 +382,7 @@ static int tc_gemm(const void* A, int64_t M, int K, const void* W, int N, const 
   p.col0 = col0;
   p.out_f32 = out_f;
   p.residual = residual;
-  return gemmtc::launch<128, kEpi>(ta, tw, p, sm_count, st);
+  return gemmtc::launch<256, kEpi, true>(ta, tw, p, sm_count, st);
 }
 
 int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode, const float* patches,

@@ -26,9 +26,6 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kThreads = 192;
 constexpr int kStagedArrays = 4;                 // per-column parameter arrays staged in smem per tile
-template <int kBlockN> constexpr int smem_bytes() {
-  return 1024 + kStages * (kABytes + kBlockN * kBlockK * 2) + 2 * kStagedArrays * kBlockN * 4 + 256;
-}
 
 struct Params {
   int64_t m;            // rows of A / C
@@ -78,34 +75,49 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
-template <int kBlockN, int kEpi>
+template <int kBlockN, int kEpi, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const Params p) {
-  constexpr int kBBytes = kBlockN * kBlockK * 2;
+  // kPair: the two CTAs of a cluster issue one cta_group::2 UMMA of M = 256 (128 rows of A per CTA) x N = kBlockN
+  // (each CTA streams half of the W tile): half the shared-memory operand traffic per SM of the 1-CTA form.
+  constexpr int kCta = kPair ? 2 : 1;
+  constexpr int kBRows = kBlockN / kCta;                 // W rows this CTA loads per stage
+  constexpr int kBBytes = kBRows * kBlockK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kNumStages = kPair ? 6 : kStages;
   constexpr int kTmemCols = 2 * kBlockN;
+  static_assert(kBRows % 128 == 0, "W is loaded in 128-row TMA boxes");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  float* epi_smem = reinterpret_cast<float*>(gen_base + kStages * kStageBytes);  // [2 buffers][kStagedArrays][kBlockN]
-  Barriers* bars = reinterpret_cast<Barriers*>(gen_base + kStages * kStageBytes + 2 * kStagedArrays * kBlockN * 4);
+  float* epi_smem = reinterpret_cast<float*>(gen_base + kNumStages * kStageBytes);  // [2][kStagedArrays][kBlockN]
+  uint64_t* bar_mem = reinterpret_cast<uint64_t*>(gen_base + kNumStages * kStageBytes + 2 * kStagedArrays * kBlockN * 4);
+  uint64_t* full_bar = bar_mem;                           // [kNumStages]
+  uint64_t* empty_bar = bar_mem + kNumStages;             // [kNumStages]
+  uint64_t* tmem_full_bar = bar_mem + 2 * kNumStages;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = static_cast<int>((p.m + kBlockM - 1) / kBlockM);
-  const int n_tiles = p.n / kBlockN;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = kPair ? (blockIdx.x >> 1) : blockIdx.x;
+  const int n_units = kPair ? (gridDim.x >> 1) : gridDim.x;
+  const int m_tiles = static_cast<int>((p.m + kBlockM * kCta - 1) / (kBlockM * kCta));
+  const int n_tiles = (p.n + kBlockN - 1) / kBlockN;
   const int total = m_tiles * n_tiles;
   const int kblocks = p.k / kBlockK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->empty[s]), 1);
+    for (int s = 0; s < kNumStages; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[s]), 4);
+      ptx::mbar_init(ptx::smem_u32(&tmem_full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tmem_empty_bar[s]), 4 * kCta);
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -114,53 +126,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_w);
   }
-  if (warp == 1) ptx::tmem_alloc<1>(ptx::smem_u32(&bars->tmem_base), kTmemCols);
+  if (warp == 1) ptx::tmem_alloc<kCta>(ptx::smem_u32(tmem_slot), kTmemCols);
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync_all(); else __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * kBlockM;
-        const int n0 = (t % n_tiles) * kBlockN;
+      for (int t = unit; t < total; t += n_units) {
+        const int m0 = (t / n_tiles) * (kBlockM * kCta) + rank * kBlockM;
+        const int n0 = (t % n_tiles) * kBlockN + rank * kBRows;
         for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, nullptr, 11);
-          const uint32_t full = ptx::smem_u32(&bars->full[stage]);
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1, nullptr, 11);
+          const uint32_t full = ptx::smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          ptx::mbar_arrive_expect_tx(full, kStageBytes);
-          ptx::tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, full);
+          if (leader) ptx::mbar_arrive_expect_tx(full, kStageBytes * kCta);
+          if (kPair) {
+            const uint32_t dst = ptx::mapa(full, 0);
+            ptx::tma_load_2d_pair(sa, &tmap_a, kb * kBlockK, m0, dst);
 #pragma unroll
-          for (int h = 0; h < kBlockN / 128; ++h)   // W tile as 128-row TMA boxes
-            ptx::tma_load_2d(sa + kABytes + h * kABytes, &tmap_w, kb * kBlockK, n0 + h * 128, full);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+            for (int h = 0; h < kBRows / 128; ++h)
+              ptx::tma_load_2d_pair(sa + kABytes + h * kABytes, &tmap_w, kb * kBlockK, n0 + h * 128, dst);
+          } else {
+            ptx::tma_load_2d(sa, &tmap_a, kb * kBlockK, m0, full);
+#pragma unroll
+            for (int h = 0; h < kBRows / 128; ++h)   // W tile as 128-row TMA boxes
+              ptx::tma_load_2d(sa + kABytes + h * kABytes, &tmap_w, kb * kBlockK, n0 + h * 128, full);
+          }
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockM, kBlockN);
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockM * kCta, kBlockN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1, nullptr, 12);
+      for (int t = unit; t < total; t += n_units) {
+        ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1, nullptr, 12);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBlockN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase, nullptr, 13);
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[stage]), phase, nullptr, 13);
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint64_t adesc = ptx::smem_desc_sw128(sa);
           const uint64_t bdesc = ptx::smem_desc_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            ptx::umma_bf16<1>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          ptx::umma_commit<1>(ptx::smem_u32(&bars->empty[stage]));
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+            ptx::umma_bf16<kCta>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit<kCta>(ptx::smem_u32(&empty_bar[stage]));
+          if (++stage == kNumStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit<1>(ptx::smem_u32(&bars->tmem_full[acc]));
+        ptx::umma_commit<kCta>(ptx::smem_u32(&tmem_full_bar[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -169,8 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quad = warp & 3;
     const int epi_tid = (warp - 2) * 32 + lane;  // 0..127
     uint32_t acc = 0, acc_phase = 0, buf = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int m0 = (t / n_tiles) * kBlockM;
+    for (int t = unit; t < total; t += n_units) {
+      const int m0 = (t / n_tiles) * (kBlockM * kCta) + rank * kBlockM;
       const int nt = t % n_tiles;
       const int n0 = nt * kBlockN;
       // stage this tile's per-column parameters in shared memory, double buffered across tiles
@@ -179,15 +199,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float* sscale = swg + kBlockN;
       float* sshift = sscale + kBlockN;
       for (int i = epi_tid; i < kBlockN; i += 128) {
-        sbias[i] = p.bias[n0 + i];
-        if (kEpi == kEpiGate || kEpi == kEpiSrGlobal) swg[i] = p.wg[n0 + i];
+        const bool in = n0 + i < p.n;
+        sbias[i] = in ? p.bias[n0 + i] : 0.f;
+        if (kEpi == kEpiGate || kEpi == kEpiSrGlobal) swg[i] = in ? p.wg[n0 + i] : 0.f;
         if (kEpi == kEpiSrGlobal) {
-          sscale[i] = p.scale[n0 + i];
-          sshift[i] = p.shift[n0 + i];
+          sscale[i] = in ? p.scale[n0 + i] : 0.f;
+          sshift[i] = in ? p.shift[n0 + i] : 0.f;
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase, nullptr, 14);
+      ptx::mbar_wait(ptx::smem_u32(&tmem_full_bar[acc]), acc_phase, nullptr, 14);
       ptx::tc_fence_after();
       const int64_t row = static_cast<int64_t>(m0) + quad * 32 + lane;
       const bool row_ok = row < p.m;
@@ -209,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ptx::tmem_ld_wait();
         if (c + 1 < kBlockN / 32) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
         const uint32_t(&cur)[32] = v[c & 1];
+        if (n0 + c * 32 >= p.n) continue;   // ragged last column tile (N % kBlockN != 0): nothing to emit
         if (kEpi == kEpiGate) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -280,35 +302,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if ((kEpi == kEpiGate || kEpi == kEpiSrLocal) && row_ok) p.partial[row * n_tiles + nt] = dot;
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
+      if (lane == 0) {
+        const uint32_t dst = ptx::smem_u32(&tmem_empty_bar[acc]);
+        if (kPair) ptx::mbar_arrive_cluster(ptx::mapa(dst, 0)); else ptx::mbar_arrive(dst);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       buf ^= 1;
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+    ptx::tmem_dealloc<kCta>(tmem_base, kTmemCols);
   }
 }
 
-template <int kBlockN, int kEpi>
+template <int kBlockN, bool kPair> constexpr int smem_bytes_v() {
+  return 1024 + (kPair ? 6 : kStages) * (kABytes + (kBlockN / (kPair ? 2 : 1)) * kBlockK * 2) +
+         2 * kStagedArrays * kBlockN * 4 + 256;
+}
+
+// number of column tiles (and of per-row partials the kEpiGate / kEpiSrLocal epilogues emit)
+template <int kBlockN> static inline int n_tiles_of(int n) { return (n + kBlockN - 1) / kBlockN; }
+
+template <int kBlockN, int kEpi, bool kPair = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const Params& p, int sm_count, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<kBlockN, kEpi>;
+  auto kern = gemm_tc_kernel<kBlockN, kEpi, kPair>;
+  constexpr int smem = smem_bytes_v<kBlockN, kPair>();
   // the opt-in shared-memory size is a per-device function attribute
   static bool configured[64] = {};
   int dev = 0;
   ERN_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kBlockN>()));
+    ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const int64_t tiles = ((p.m + kBlockM - 1) / kBlockM) * (p.n / kBlockN);
-  const int grid = static_cast<int>(tiles < sm_count ? tiles : sm_count);
-  kern<<<grid, kThreads, smem_bytes<kBlockN>(), st>>>(ta, tw, p);
-  ERN_CUDA(cudaGetLastError());
+  constexpr int kCta = kPair ? 2 : 1;
+  const int64_t tiles = ((p.m + kBlockM * kCta - 1) / (kBlockM * kCta)) * n_tiles_of<kBlockN>(p.n);
+  int units = kPair ? sm_count / 2 : sm_count;
+  if (tiles < units) units = static_cast<int>(tiles);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(units * kCta);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ERN_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, p));
   return ERN_OK;
 }
 

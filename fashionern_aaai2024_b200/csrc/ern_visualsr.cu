@@ -135,7 +135,7 @@ __global__ void finalize_kernel(const float* __restrict__ local, int64_t rows, i
 }
 
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
-constexpr int kTcBlockN = 128;
+constexpr int kTcBlockN = 256;   // CTA-pair tiles; a ragged last column tile (D = 640) is masked in the epilogue
 
 size_t packed_bytes(int dim) { return al(static_cast<size_t>(dim) * dim * 2) * 2 + 256; }
 
@@ -150,7 +150,7 @@ int pack(const ern_visualsr_weights* w, int dim, void* packed, cudaStream_t st) 
 size_t workspace_bytes(int64_t rows, int patches, int dim, int mode) {
   const size_t r = rows, P = patches, d = dim;
   if (mode == ERN_MODE_FP32) return al(r * d * 4) * 2 + al(r * P * cdiv(dim, kTile) * 4) + 512;
-  return al(r * P * d * 2) + al(r * d * 2) + al(r * d * 4) + al(r * P * (d / kTcBlockN) * 4) + 512;
+  return al(r * P * d * 2) + al(r * d * 2) + al(r * d * 4) + al(r * P * gemmtc::n_tiles_of<kTcBlockN>(dim) * 4) + 512;
 }
 
 int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const float* local, int64_t rows,
@@ -181,7 +181,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
   __nv_bfloat16* mean_b = reinterpret_cast<__nv_bfloat16*>(ws + al(r * P * d * 2));
   float* cvec = reinterpret_cast<float*>(ws + al(r * P * d * 2) + al(r * d * 2));
   float* partial = reinterpret_cast<float*>(ws + al(r * P * d * 2) + al(r * d * 2) + al(r * d * 4));
-  const int n_tiles = dim / kTcBlockN;
+  const int n_tiles = gemmtc::n_tiles_of<kTcBlockN>(dim);
   const uint8_t* pk = static_cast<const uint8_t*>(w->packed_bf16);
   const void* wl_b = pk;
   const void* wg_b = pk + al(d * d * 2);
@@ -203,7 +203,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
   g.shift = w->bn_global_shift;
   g.out_f32 = cvec;
   g.ldo = dim;
-  if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrGlobal>(t_mean, t_wg, g, sm_count, st))) return rc;
+  if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrGlobal, true>(t_mean, t_wg, g, sm_count, st))) return rc;
   gemmtc::Params l{};
   l.m = rows * patches;
   l.n = dim;
@@ -214,7 +214,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
   l.cvec = cvec;
   l.patches = patches;
   l.partial = partial;
-  if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrLocal>(t_local, t_wl, l, sm_count, st))) return rc;
+  if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrLocal, true>(t_local, t_wl, l, sm_count, st))) return rc;
   finalize_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, partial, n_tiles, w->b_common, out);
   ERN_CUDA(cudaGetLastError());
   return ERN_OK;
