@@ -26,6 +26,8 @@ constexpr int kStages = 4;
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kThreads = 192;
 constexpr int kStagedArrays = 4;                 // per-column parameter arrays staged in smem per tile
+constexpr int kStgPitch = 128 + 16;              // per-warp store-transpose buffer: 32 rows x 128 B, padded
+constexpr int kStgWarpBytes = 32 * kStgPitch;
 
 struct Params {
   int64_t m;            // rows of A / C
@@ -92,7 +94,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   float* epi_smem = reinterpret_cast<float*>(gen_base + kNumStages * kStageBytes);  // [2][kStagedArrays][kBlockN]
-  uint64_t* bar_mem = reinterpret_cast<uint64_t*>(gen_base + kNumStages * kStageBytes + 2 * kStagedArrays * kBlockN * 4);
+  uint8_t* stage_smem = gen_base + kNumStages * kStageBytes + 2 * kStagedArrays * kBlockN * 4;   // [4 warps][kStgWarpBytes]
+  uint64_t* bar_mem = reinterpret_cast<uint64_t*>(stage_smem + 4 * kStgWarpBytes);
   uint64_t* full_bar = bar_mem;                           // [kNumStages]
   uint64_t* empty_bar = bar_mem + kNumStages;             // [kNumStages]
   uint64_t* tmem_full_bar = bar_mem + 2 * kNumStages;     // [2]
@@ -223,79 +226,125 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         row_shift = p.shift[pidx];
         crow = p.cvec + (rr / p.patches) * p.n + n0;
       }
-      uint32_t v[2][32];
-      ptx::tmem_ld_32x32(taddr, v[0]);
-#pragma unroll
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        ptx::tmem_ld_wait();
-        if (c + 1 < kBlockN / 32) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-        const uint32_t(&cur)[32] = v[c & 1];
-        if (n0 + c * 32 >= p.n) continue;   // ragged last column tile (N % kBlockN != 0): nothing to emit
-        if (kEpi == kEpiGate) {
+      // The chunk loops are deliberately rolled: unrolling 8 chunks x 32 elements of epilogue math made a 116 KB
+      // kernel that stalled on instruction fetch (ncu: stall_no_inst top, 20 % tensor pipe on the GELU GEMM).
+      // Stores go through a per-warp shared-memory transpose: a thread owns one output ROW, so direct stores would
+      // touch 32 different 128-byte lines per instruction (ncu: 32 sectors/request); after the transpose every
+      // store instruction writes 4 complete lines.
+      uint8_t* stg = stage_smem + (warp - 2) * kStgWarpBytes;
+      const int64_t row_base = static_cast<int64_t>(m0) + quad * 32;
+      const int srow = lane >> 3, spiece = lane & 7;
+      if (kEpi == kEpiStoreRelu || kEpi == kEpiBiasBf16 || kEpi == kEpiGeluBf16) {
+#pragma unroll 1
+        for (int g = 0; g < kBlockN / 64; ++g) {
+          if (n0 + g * 64 >= p.n) break;     // ragged last column tile: nothing more to emit
+          uint32_t lo[32], hi[32];
+          ptx::tmem_ld_32x32(taddr + g * 64, lo);
+          ptx::tmem_ld_32x32(taddr + g * 64 + 32, hi);
+          ptx::tmem_ld_wait();
+          uint32_t packed[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float h = fmaxf(__uint_as_float(cur[j]) + sbias[c * 32 + j], 0.f);
-            dot = fmaf(h, swg[c * 32 + j], dot);
-          }
-        } else if (kEpi == kEpiSrLocal) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cv = *reinterpret_cast<const float4*>(crow + c * 32 + j4 * 4);
-            const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              const float h = tanh_fast(fmaf(row_scale, __uint_as_float(cur[j]) + sbias[c * 32 + j], row_shift));
-              dot = fmaf(h, cc[e], dot);
+            const int cidx = g * 64 + 2 * j;
+            float x0 = __uint_as_float(j < 16 ? lo[2 * j] : hi[2 * j - 32]) + sbias[cidx];
+            float x1 = __uint_as_float(j < 16 ? lo[2 * j + 1] : hi[2 * j - 31]) + sbias[cidx + 1];
+            if (kEpi == kEpiStoreRelu) {
+              x0 = fmaxf(x0, 0.f);
+              x1 = fmaxf(x1, 0.f);
+            } else if (kEpi == kEpiGeluBf16) {
+              x0 = gelu_erf_fast(x0);
+              x1 = gelu_erf_fast(x1);
             }
+            packed[j] = pack_bf16x2(x0, x1);
           }
-        } else if (kEpi == kEpiSrGlobal) {
-          if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + row * p.ldo + n0 + c * 32);
+          uint4* mine = reinterpret_cast<uint4*>(stg + lane * kStgPitch);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) mine[q4] = make_uint4(packed[4 * q4], packed[4 * q4 + 1], packed[4 * q4 + 2], packed[4 * q4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = srow + 4 * it;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * kStgPitch + spiece * 16);
+            if (row_base + r < p.m)
+              *reinterpret_cast<uint4*>(p.out + (row_base + r) * p.ldo + p.col0 + n0 + g * 64 + spiece * 8) = val;
+          }
+          __syncwarp();
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < kBlockN / 32; ++c) {
+          if (n0 + c * 32 >= p.n) break;
+          uint32_t cur[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, cur);
+          ptx::tmem_ld_wait();
+          if (kEpi == kEpiGate) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float h = fmaxf(__uint_as_float(cur[j]) + sbias[c * 32 + j], 0.f);
+              dot = fmaf(h, swg[c * 32 + j], dot);
+            }
+          } else if (kEpi == kEpiSrLocal) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-              float o[4];
+              const float4 cv = *reinterpret_cast<const float4*>(crow + c * 32 + j4 * 4);
+              const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int j = c * 32 + j4 * 4 + e;
-                o[e] = tanh_fast(fmaf(sscale[j], __uint_as_float(cur[j4 * 4 + e]) + sbias[j], sshift[j])) * swg[j];
+                const int j = j4 * 4 + e;
+                const float h = tanh_fast(fmaf(row_scale, __uint_as_float(cur[j]) + sbias[c * 32 + j], row_shift));
+                dot = fmaf(h, cc[e], dot);
               }
-              dst[j4] = make_float4(o[0], o[1], o[2], o[3]);
             }
-          }
-        } else if (kEpi == kEpiResidF32) {
-          if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + row * p.ldo + n0 + c * 32);
-            const float4* res = p.residual ? reinterpret_cast<const float4*>(p.residual + row * p.ldo + n0 + c * 32) : nullptr;
+          } else {
+            // fp32 row outputs (kEpiResidF32 / kEpiSrGlobal): 32 columns = one 128-byte line per row
+            float o[32];
+            if (kEpi == kEpiResidF32) {
+              if (p.residual) {
+                // coalesced read of the residual tile, transposed through shared memory to row ownership
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 r4 = res ? res[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
-              const int j = c * 32 + j4 * 4;
-              dst[j4] = make_float4(__uint_as_float(cur[j4 * 4 + 0]) + sbias[j + 0] + r4.x,
-                                    __uint_as_float(cur[j4 * 4 + 1]) + sbias[j + 1] + r4.y,
-                                    __uint_as_float(cur[j4 * 4 + 2]) + sbias[j + 2] + r4.z,
-                                    __uint_as_float(cur[j4 * 4 + 3]) + sbias[j + 3] + r4.w);
+                for (int it = 0; it < 8; ++it) {
+                  const int r = srow + 4 * it;
+                  uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                  if (row_base + r < p.m)
+                    val = *reinterpret_cast<const uint4*>(p.residual + (row_base + r) * p.ldo + n0 + c * 32 + spiece * 4);
+                  *reinterpret_cast<uint4*>(stg + r * kStgPitch + spiece * 16) = val;
+                }
+                __syncwarp();
+                const float4* mine_r = reinterpret_cast<const float4*>(stg + lane * kStgPitch);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                  const float4 r4 = mine_r[q4];
+                  o[4 * q4 + 0] = r4.x;
+                  o[4 * q4 + 1] = r4.y;
+                  o[4 * q4 + 2] = r4.z;
+                  o[4 * q4 + 3] = r4.w;
+                }
+                __syncwarp();
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(cur[j]) + sbias[c * 32 + j] + o[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int cj = c * 32 + j;
+                o[j] = tanh_fast(fmaf(sscale[cj], __uint_as_float(cur[j]) + sbias[cj], sshift[cj])) * swg[cj];
+              }
             }
-          }
-        } else {
-          uint32_t packed[16];
+            float4* mine = reinterpret_cast<float4*>(stg + lane * kStgPitch);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = __uint_as_float(cur[2 * j]) + sbias[c * 32 + 2 * j];
-            float b = __uint_as_float(cur[2 * j + 1]) + sbias[c * 32 + 2 * j + 1];
-            if (kEpi == kEpiStoreRelu) {
-              a = fmaxf(a, 0.f);
-              b = fmaxf(b, 0.f);
-            } else if (kEpi == kEpiGeluBf16) {
-              a = gelu_erf_fast(a);
-              b = gelu_erf_fast(b);
+            for (int q4 = 0; q4 < 8; ++q4) mine[q4] = make_float4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = srow + 4 * it;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * kStgPitch + spiece * 16);
+              if (row_base + r < p.m)
+                *reinterpret_cast<uint4*>(p.out_f32 + (row_base + r) * p.ldo + n0 + c * 32 + spiece * 4) = val;
             }
-            packed[j] = pack_bf16x2(a, b);
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.ldo + p.col0 + n0 + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            __syncwarp();
           }
         }
       }
@@ -321,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 template <int kBlockN, bool kPair> constexpr int smem_bytes_v() {
   return 1024 + (kPair ? 6 : kStages) * (kABytes + (kBlockN / (kPair ? 2 : 1)) * kBlockK * 2) +
-         2 * kStagedArrays * kBlockN * 4 + 256;
+         2 * kStagedArrays * kBlockN * 4 + 4 * kStgWarpBytes + 256;
 }
 
 // number of column tiles (and of per-row partials the kEpiGate / kEpiSrLocal epilogues emit)
