@@ -213,6 +213,169 @@ attention_kernel(const T* __restrict__ Q, int64_t ldq, const T* __restrict__ K, 
   }
 }
 
+// ---- bf16 attention on the (legacy) warp-level tensor path -------------------------------------------------------
+// One block per (batch element, head); warp w owns score rows [16w, 16w+16).  S = Q K^T and O = P V are
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32); the softmax runs on the accumulator fragments and its output is re-used
+// directly as the A fragments of the second product (no shared-memory round trip).  L <= 96, head size 64 or 80.
+// tcgen05 is not used here: a 91 x 91 x 80 problem per head cannot fill a 128-row UMMA tile.
+constexpr int kAttnLmax = 96;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int kDh>
+__global__ void __launch_bounds__(192)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfloat16* __restrict__ K, int64_t ldk,
+                     const __nv_bfloat16* __restrict__ V, int64_t ldv, __nv_bfloat16* __restrict__ O, int64_t ldo,
+                     int Lq, int Lk, float scale) {
+  constexpr int QP = kDh + 8;          // row pitch (bf16) of Qs / Ks: 12 g + t bank pattern, conflict-free fragments
+  constexpr int VP = kAttnLmax + 8;    // row pitch of the transposed V
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* Ks = Qs + kAttnLmax * QP;
+  __nv_bfloat16* Vt = Ks + kAttnLmax * QP;   // [kDh][VP]
+  const int h = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int tid = threadIdx.x;
+  constexpr int kVpr = kDh / 8;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < kAttnLmax * kVpr; e += 192) {
+    const int r = e / kVpr, v = e - r * kVpr;
+    uint4 q4 = zero4, k4 = zero4, v4 = zero4;
+    if (r < Lq) q4 = *reinterpret_cast<const uint4*>(Q + (b * Lq + r) * ldq + h * kDh + v * 8);
+    if (r < Lk) {
+      k4 = *reinterpret_cast<const uint4*>(K + (b * Lk + r) * ldk + h * kDh + v * 8);
+      v4 = *reinterpret_cast<const uint4*>(V + (b * Lk + r) * ldv + h * kDh + v * 8);
+    }
+    *reinterpret_cast<uint4*>(Qs + r * QP + v * 8) = q4;
+    *reinterpret_cast<uint4*>(Ks + r * QP + v * 8) = k4;
+    const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(&v4);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) Vt[(v * 8 + u) * VP + r] = vv[u];
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+  if (m0 >= Lq) return;
+  const int ntiles = (Lk + 7) >> 3;      // 8-column score tiles
+  const int ktiles = (Lk + 15) >> 4;     // 16-deep steps of P V
+
+  float sacc[12][4];
+#pragma unroll
+  for (int nt = 0; nt < 12; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < kDh / 16; ++kk) {
+    uint32_t a[4];
+    a[0] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g) * QP + kk * 16 + 2 * t);
+    a[1] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g + 8) * QP + kk * 16 + 2 * t);
+    a[2] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g) * QP + kk * 16 + 2 * t + 8);
+    a[3] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g + 8) * QP + kk * 16 + 2 * t + 8);
+#pragma unroll
+    for (int nt = 0; nt < 12; ++nt) {
+      if (nt < ntiles) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * QP + kk * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * QP + kk * 16 + 2 * t + 8);
+        mma_bf16_16816(sacc[nt], a, b0, b1);
+      }
+    }
+  }
+  // softmax over the Lk valid columns of rows (m0+g) [regs 0,1] and (m0+g+8) [regs 2,3]
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < 12; ++nt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = nt * 8 + 2 * t + (i & 1);
+      const float v = (nt < ntiles && col < Lk) ? sacc[nt][i] * scale : -INFINITY;
+      sacc[nt][i] = v;
+      if (i < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+    }
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 12; ++nt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float e = __expf(sacc[nt][i] - (i < 2 ? mx0 : mx1));   // exp(-inf) = 0 for masked columns
+      sacc[nt][i] = e;
+      if (i < 2) sum0 += e; else sum1 += e;
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+
+  float oacc[kDh / 8][4];
+#pragma unroll
+  for (int dn = 0; dn < kDh / 8; ++dn)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oacc[dn][i] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 6; ++kt) {
+    if (kt < ktiles) {
+      uint32_t a[4];
+      a[0] = pack2_bf16(sacc[2 * kt][0] * inv0, sacc[2 * kt][1] * inv0);
+      a[1] = pack2_bf16(sacc[2 * kt][2] * inv1, sacc[2 * kt][3] * inv1);
+      a[2] = pack2_bf16(sacc[2 * kt + 1][0] * inv0, sacc[2 * kt + 1][1] * inv0);
+      a[3] = pack2_bf16(sacc[2 * kt + 1][2] * inv1, sacc[2 * kt + 1][3] * inv1);
+#pragma unroll
+      for (int dn = 0; dn < kDh / 8; ++dn) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Vt + (dn * 8 + g) * VP + kt * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vt + (dn * 8 + g) * VP + kt * 16 + 2 * t + 8);
+        mma_bf16_16816(oacc[dn], a, b0, b1);
+      }
+    }
+  }
+  const int r0 = m0 + g, r1 = m0 + g + 8;
+#pragma unroll
+  for (int dn = 0; dn < kDh / 8; ++dn) {
+    const int col = h * kDh + dn * 8 + 2 * t;
+    if (r0 < Lq) *reinterpret_cast<uint32_t*>(O + (b * Lq + r0) * ldo + col) = pack2_bf16(oacc[dn][0], oacc[dn][1]);
+    if (r1 < Lq) *reinterpret_cast<uint32_t*>(O + (b * Lq + r1) * ldo + col) = pack2_bf16(oacc[dn][2], oacc[dn][3]);
+  }
+}
+
+template <int kDh>
+static int launch_attention_mma(const __nv_bfloat16* Q, int64_t ldq, const __nv_bfloat16* K, int64_t ldk,
+                                const __nv_bfloat16* V, int64_t ldv, __nv_bfloat16* O, int64_t ldo, int64_t batch,
+                                int heads, int Lq, int Lk, cudaStream_t st) {
+  constexpr size_t smem = (2 * kAttnLmax * (kDh + 8) + kDh * (kAttnLmax + 8)) * 2;
+  auto kern = attention_mma_kernel<kDh>;
+  static bool configured[64] = {};
+  int dev = 0;
+  ERN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(kDh));
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    kern<<<dim3(heads, static_cast<unsigned>(nb)), 192, smem, st>>>(Q + b0 * Lq * ldq, ldq, K + b0 * Lk * ldk, ldk,
+                                                                   V + b0 * Lk * ldv, ldv, O + b0 * Lq * ldo, ldo, Lq, Lk,
+                                                                   scale);
+  }
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
+}
+
 // One block per batch element: F.normalize of the patch / token states (models/fusion_model.py:38-41), the first P
 // normalised token rows (the only cross-attention queries used, :47) and seq_text_mean (:49).
 template <typename T>
@@ -342,6 +505,13 @@ size_t workspace_bytes(int64_t batch, int P, int T, int dim, int inter, int mode
 template <typename T>
 static int run_attention(const T* Q, int64_t ldq, const T* K, int64_t ldk, const T* V, int64_t ldv, T* O, int64_t ldo,
                          int64_t batch, int heads, int Lq, int Lk, int dh, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    const bool vec_ok = (ldq % 8 == 0) && (ldk % 8 == 0) && (ldv % 8 == 0) && (ldo % 2 == 0);
+    if (vec_ok && Lq <= kAttnLmax && Lk <= kAttnLmax) {
+      if (dh == 80) return launch_attention_mma<80>(Q, ldq, K, ldk, V, ldv, O, ldo, batch, heads, Lq, Lk, st);
+      if (dh == 64) return launch_attention_mma<64>(Q, ldq, K, ldk, V, ldv, O, ldo, batch, heads, Lq, Lk, st);
+    }
+  }
   ERN_REQUIRE(dh % (16 / static_cast<int>(sizeof(T))) == 0 && (ldq * sizeof(T)) % 16 == 0 && (ldk * sizeof(T)) % 16 == 0 &&
                   (ldv * sizeof(T)) % 16 == 0,
               "attention: head size and row strides must allow 16-byte loads (dh = %d)", dh);
