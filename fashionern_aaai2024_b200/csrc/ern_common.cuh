@@ -106,12 +106,6 @@ __device__ __forceinline__ void sink_put_atomic(const CandidateSink& s, int64_t 
   if (pos < s.seg_size) s.lists[q * s.cap + s.keep + pos] = make_key(value, gid);
 }
 
-// ---- launch-plan helpers shared by the C ABI ---------------------------------------------------------
-struct Phase {
-  int64_t begin, end;
-  int dense;
-};
-
 inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace ern

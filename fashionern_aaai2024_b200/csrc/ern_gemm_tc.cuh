@@ -1,8 +1,13 @@
 // Persistent warp-specialised tcgen05 GEMM   C = A . W^T   (A [M,K], W [N,K] bf16 K-major, fp32 accumulate in TMEM)
-// with fused epilogues, shared by the fusion head (ern_combiner_tc.cu) and VisualSR (ern_visualsr.cu).
-//   TMA producer warp -> kStages ring of {128 x 64 A tile, kBlockN x 64 W tile} (128B swizzle)
-//   one elected thread issues tcgen05.mma (M = 128, N = kBlockN, K = 16); accumulators double buffered in TMEM
-//   4 epilogue warps: tcgen05.ld 32 columns at a time, one output row per thread
+// with fused epilogues, shared by the fusion head (ern_combiner_tc.cu), VisualSR (ern_visualsr.cu) and the DVR
+// encoder (ern_dvr.cu).
+//   TMA producer warp -> ring of {128 x 64 A tile, W tile} stages (128B swizzle)
+//   kPair (the mode every caller uses): the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 of
+//     M = 256 (128 rows of A per CTA) x N = 256 (each CTA streams half of the W tile) x K = 16 -- 256 x 256 tiles,
+//     6-stage ring; 1-CTA mode: M = 128, N = kBlockN, 4 stages
+//   accumulators double buffered in TMEM (2 x kBlockN columns)
+//   4 epilogue warps per CTA: tcgen05.ld 32 columns at a time, one output row per thread, rolled chunk loop,
+//     per-warp shared-memory transpose so that global stores / residual loads are full 128-byte lines
 #pragma once
 #include "ern_internal.cuh"
 #include "ern_ptx.cuh"
@@ -44,14 +49,6 @@ struct Params {
   const float* cvec;    // [M / P, N]         kEpiSrLocal
   int patches;          // P
   const float* residual;  // [M, ldo] fp32     kEpiResidF32 (nullable)
-};
-
-struct Barriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
-  uint32_t tmem_base;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

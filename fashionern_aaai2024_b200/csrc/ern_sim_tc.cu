@@ -12,8 +12,10 @@
 //          N = 256 (each CTA streams half of the gallery tile), halving shared-memory operand traffic.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer (leader CTA only
 // in a pair), warps 2..5 = epilogue; epilogue thread (quadrant, lane) owns one query row: it reads the
-// row's scores with tcgen05.ld (32 columns at a time), max-reduces them and only walks the 32 values
-// when the maximum reaches the row's threshold.
+// row's scores with tcgen05.ld (32 columns at a time), max-reduces them (FMNMX3) and only when the maximum reaches
+// the row's threshold walks a bit-mask of the 32 compares, appending survivors with a private cursor into the
+// list segment this work item owns (no atomics).  The epilogue is deliberately compact code (rolled chunk loop).
+// Environment knobs (profiling aids, read once): ERN_FORCE_SINGLE_CTA=1, ERN_PREFETCH_TILES=n, ERN_DEBUG_FLAGS.
 #include "ern_common.cuh"
 #include "ern_ptx.cuh"
 
