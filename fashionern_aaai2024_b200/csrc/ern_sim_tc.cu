@@ -378,7 +378,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, in
   if (dbg < 0) { const char* e = getenv("ERN_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
   static int pf = -1;
-  if (pf < 0) { const char* e = getenv("ERN_PREFETCH_TILES"); pf = e ? atoi(e) : 4; }
+  if (pf < 0) { const char* e = getenv("ERN_PREFETCH_TILES"); pf = e ? atoi(e) : 0; }
   p.gallery_base = (ldg == dim) ? static_cast<const uint8_t*>(gallery) : nullptr;
   p.gallery_rows = gallery_rows;
   p.row_bytes = dim * 2;
