@@ -95,3 +95,26 @@ def test_accelerate_ern_swaps_reference_modules_and_keeps_weights():
     assert set(after.keys()) == set(before.keys())             # checkpoints stay loadable both ways
     assert all(torch.equal(after[k], before[k]) for k in before)
     assert not model.Combiner_module.training                   # eval flag preserved
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ern_b200.h must be consumable by a C compiler (the boundary is a C ABI, not C++) and every declared
+    function must resolve against the built library."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    calls = "\n".join(f"  p[{i}] = (fn_t)&{name};" for i, name in enumerate(_lib.SYMBOLS))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ern_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t p[%d];\n%s\n'
+                   '  printf("%%d %%d\\n", ern_version(), (int)sizeof(ern_dvr_weights));\n  return p[0] == 0;\n}\n'
+                   % (len(_lib.SYMBOLS), calls))
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-l:libern_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) >= 100
+    # the ctypes mirror of the largest struct must have the C layout
+    import ctypes
+    assert int(out[1]) == ctypes.sizeof(_lib.DvrWeights)

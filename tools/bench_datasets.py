@@ -1,0 +1,53 @@
+"""Scoring tail at the dataset shapes of BASELINE.json configs 1-4 (top-50): B200 path vs the reference-faithful
+CPU path (fp32 matmul + FULL argsort + id membership, oracle port) on the same synthetic features."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import fashionern_aaai2024_b200 as ern  # noqa: E402
+from fashionern_aaai2024_b200 import synthetic as syn  # noqa: E402
+from oracle import ern_oracle as orc  # noqa: E402
+
+SHAPES = [("config1/2 FashionIQ dress (640-d)", 2017, 3817, 640), ("config2 FashionIQ shirt (512-d)", 2038, 6346, 512),
+          ("config2 FashionIQ toptee (512-d)", 1961, 5373, 512), ("Shoes val (640-d)", 1761, 4658, 640),
+          ("config4 CIRR val (640-d)", 4181, 2297, 640), ("config3 Fashion200k (640-d)", 33480, 29789, 640)]
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.set_num_threads(os.cpu_count())
+    for name, q, n, dim in SHAPES:
+        pred, gal = syn.features(1, q, dim, unit=True), syn.features(2, n, dim, unit=True)
+        tgt = torch.randint(0, n, (q,), generator=torch.Generator().manual_seed(3))
+        cls = torch.arange(n, dtype=torch.int32, device=dev)
+        pd, gd, td = pred.to(dev), gal.to(dev), tgt.int().to(dev)
+        res = {}
+        for prec in ("bf16", "fp32"):
+            for _ in range(3):
+                ern.score_topk_recall(pd, gd, cls, td, (10, 50), precision=prec)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            iters = 10
+            for _ in range(iters):
+                r = ern.score_topk_recall(pd, gd, cls, td, (10, 50), precision=prec)     # includes the hit-count D2H
+            torch.cuda.synchronize()
+            res[prec] = (time.perf_counter() - t0) / iters
+        t0 = time.perf_counter()
+        d = orc.distances(pred, gal)
+        order = torch.argsort(d, dim=-1)
+        ranks = orc.first_hit_rank(order[:, :50], np.arange(n), tgt.numpy())
+        _ = orc.recall_at(ranks, (10, 50))
+        cpu = time.perf_counter() - t0
+        print(json.dumps({"shape": name, "queries": q, "gallery": n, "dim": dim,
+                          "b200_bf16_ms": res["bf16"] * 1e3, "b200_fp32_validation_ms": res["fp32"] * 1e3,
+                          "b200_bf16_queries_per_s": q / res["bf16"], "cpu_reference_ms": cpu * 1e3,
+                          "cpu_cores": os.cpu_count(), "cpu_queries_per_s": q / cpu}))
+
+
+if __name__ == "__main__":
+    main()
