@@ -1,0 +1,53 @@
+"""GPU: randomized shapes through ern_sim_topk (both arithmetic modes, both rankings, exclusion, odd sizes around
+the tile / phase / chunk boundaries), each checked against the CPU oracle.  Seeds are fixed: the cases are
+deterministic."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ern_oracle as orc
+from fashionern_aaai2024_b200 import ops, synthetic as syn
+from fashionern_aaai2024_b200._lib import MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARITY
+
+pytestmark = pytest.mark.gpu
+
+
+def cases():
+    rng = np.random.default_rng(20241017)
+    special_n = [1, 2, 127, 128, 129, 255, 256, 257, 511, 2047, 2048, 2049, 2303, 16383, 16384, 16385, 40001]
+    special_q = [1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 383, 384, 385, 1000]
+    out = []
+    for i in range(36):
+        q = int(rng.choice(special_q))
+        n = int(rng.choice(special_n)) if i % 3 else int(rng.integers(1, 30000))
+        dim = int(rng.choice([64, 128, 192, 256, 320, 512, 576, 640]))
+        k = int(rng.choice([1, 5, 10, 50, 51, 100, 127, 128]))
+        mode = MODE_BF16 if i % 4 else MODE_FP32
+        rank_by = RANK_REFERENCE if i % 2 else RANK_SIMILARITY
+        out.append((i, q, n, dim, k, mode, rank_by, bool(i % 5 == 0), int(rng.choice([8, 8, 2, 16, 1]))))
+    return out
+
+
+@pytest.mark.parametrize("i,q,n,dim,k,mode,rank_by,use_excl,growth", cases())
+def test_random_shape_matches_oracle(cuda_device, i, q, n, dim, k, mode, rank_by, use_excl, growth):
+    pred, gal = syn.features(1000 + i, q, dim, unit=True), syn.features(2000 + i, n, dim, unit=True)
+    excl = None
+    if use_excl:
+        excl = torch.randint(-1, n, (q,), generator=torch.Generator().manual_seed(3000 + i))
+    if mode == MODE_BF16:
+        po, go = pred.bfloat16().float(), gal.bfloat16().float()
+        qd, gd = pred.bfloat16().to(cuda_device), gal.bfloat16().to(cuda_device)
+    else:
+        po, go = pred, gal
+        qd, gd = pred.to(cuda_device), gal.to(cuda_device)
+    vals, ids, keys, status = ops.sim_topk(qd, gd, k, mode=mode, rank_by=rank_by, growth=growth, want_keys=True,
+                                           exclude_ids=None if excl is None else excl.to(cuda_device))
+    assert int(status[0].item()) == 0
+    v = vals.cpu().numpy()
+    sims = np.where(np.isfinite(v), v + (1.0 if rank_by == RANK_REFERENCE else 0.0), 0.0)
+    orc.compare_topk(ids.cpu().numpy(), sims, po, go, k, tol=2.2e-6, exclude_index=excl)
+    # keys are the wire format: they must decode to the same (value, id) pairs
+    kk = keys.cpu().numpy().astype(np.uint64)
+    dec_ids = (np.uint64(0xFFFFFFFF) - (kk & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    valid = ids.cpu().numpy() >= 0
+    assert np.array_equal(dec_ids[valid], ids.cpu().numpy()[valid].astype(np.int64)) and np.all(kk[~valid] == 0)
