@@ -181,3 +181,37 @@ def test_split_cirr_subset_equals_fused(cuda_device):
         c_s, r_s = ops.cirr_subset_from_scores(total, members, ref, tgt, (1, 2, 3))
         assert torch.equal(r_f, r_s) and torch.equal(c_f, c_s)
         assert bool((r_s >= 0).all()) and 0 < int(c_s[0]) < q
+
+
+def test_cuda_graph_capture_of_the_tail(cuda_device):
+    """Every C-ABI call is stream-ordered and allocation-free, so the whole tail (cast -> scoring/top-k -> recall)
+    can be captured once in a CUDA graph and replayed on new data (launch-bound dataset-scale shapes)."""
+    q, n, dim, k = 500, 4000, 640, 50
+    pred_s, gal_s = torch.empty(q, dim, device=cuda_device), torch.empty(n, dim, device=cuda_device)
+    cls = torch.arange(n, dtype=torch.int32, device=cuda_device)
+    tgt_s = torch.zeros(q, dtype=torch.int32, device=cuda_device)
+
+    def tail():
+        _, qb = ops.l2norm_rows(pred_s, normalize=False, want_f32=False, want_bf16=True)
+        _, gb = ops.l2norm_rows(gal_s, normalize=False, want_f32=False, want_bf16=True)
+        vals, ids, _, status = ops.sim_topk(qb, gb, k, check_overflow=False)
+        counts, ranks = ops.recall_at_k(ids, cls, tgt_s, (1, 10, 50))
+        return vals, ids, counts, status
+
+    pred_s.copy_(unit(61, q, dim)); gal_s.copy_(unit(62, n, dim))
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            tail()                                   # warm-up outside capture (lazy kernel attributes, entry points)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_vals, g_ids, g_counts, g_status = tail()
+    for seed in (63, 65):
+        pred_s.copy_(unit(seed, q, dim)); gal_s.copy_(unit(seed + 1, n, dim))
+        tgt_s.copy_(torch.randint(0, n, (q,), generator=torch.Generator().manual_seed(seed)).int())
+        graph.replay()
+        torch.cuda.synchronize()
+        e_vals, e_ids, e_counts, _ = tail()
+        assert torch.equal(g_ids, e_ids) and torch.equal(g_vals, e_vals) and torch.equal(g_counts, e_counts)
+        assert int(g_status[0].item()) == 0
