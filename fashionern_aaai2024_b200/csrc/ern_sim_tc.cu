@@ -6,7 +6,7 @@
 //
 // Shape of the computation per CTA (or CTA pair, kPair):
 //   A = 128 queries x D bf16, RESIDENT in shared memory for a whole work item (160 KB at D = 640),
-//   B = gallery rows streamed by TMA in 128-row x 64-column (16 KB, 128B-swizzled) stages, 4-deep ring,
+//   B = gallery rows streamed by TMA in 128-row x 64-column (16 KB, 128B-swizzled) stages; ring depth = 14 - D/64 (4 at D = 640, 6 at D = 512),
 //   D = 128 x TILE_G fp32 accumulator in TMEM, double buffered (2 x TILE_G columns),
 //   kPair: the two CTAs of a cluster issue ONE cta_group::2 UMMA of M = 256 (128 queries per CTA) by
 //          N = 256 (each CTA streams half of the gallery tile), halving shared-memory operand traffic.
@@ -25,11 +25,12 @@ namespace simtc {
 constexpr int kBlockQ = 128;
 constexpr int kBlockG = 128;
 constexpr int kBlockK = 64;
-constexpr int kStages = 4;
-constexpr int kMaxKBlocks = 10;
+constexpr int kMaxKBlocks = 10;      // D <= 640 resident
+constexpr int kTotalTiles = 14;      // 16 KB smem tiles: num_kblocks hold the query tile, the rest is the gallery ring
+constexpr int kMaxStages = 12;       // (D = 640 -> 4 stages, D = 512 -> 6, D <= 128 -> 12)
 constexpr int kTileBytes = kBlockQ * kBlockK * 2;  // 16 KB: one 128 x 64 bf16 swizzled tile
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = 1024 + (kMaxKBlocks + kStages) * kTileBytes + 256;
+constexpr int kSmemBytes = 1024 + kTotalTiles * kTileBytes + 512;
 
 struct Params {
   CandidateSink sink;
@@ -46,8 +47,8 @@ struct Params {
 };
 
 struct Barriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
   uint64_t a_full;
   uint64_t a_empty;
   uint64_t tmem_full[2];
@@ -67,8 +68,9 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + kMaxKBlocks * kTileBytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_raw + (smem_b + kStages * kTileBytes - ptx::smem_u32(smem_raw)));
+  const uint32_t smem_b = smem_base + p.num_kblocks * kTileBytes;
+  const uint32_t kStages = min(kTotalTiles - p.num_kblocks, kMaxStages);   // deeper gallery ring for smaller D
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_raw + (smem_base + kTotalTiles * kTileBytes - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +82,7 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   int32_t* status = p.sink.status;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->empty[s]), 1);
     }
