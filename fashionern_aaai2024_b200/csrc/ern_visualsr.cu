@@ -18,7 +18,7 @@ namespace visualsr {
 
 constexpr int kMaxPatches = 32;
 
-// one warp per row b: mean over patches (+ bf16 copies of the patch matrix and of the mean for the GEMMs)
+// one warp per row b: mean over patches (+ bf16 copies of the patch matrix and of the mean for the GEMMs); HBM-bound
 __global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, int patches, int dim,
                                float* __restrict__ mean_f32, __nv_bfloat16* __restrict__ mean_b,
                                __nv_bfloat16* __restrict__ local_b) {
@@ -26,6 +26,29 @@ __global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, in
   const int lane = threadIdx.x & 31;
   if (b >= rows) return;
   const float* x = local + b * patches * dim;
+  const float inv = static_cast<float>(patches);
+  if ((dim & 3) == 0) {
+    for (int d = lane * 4; d < dim; d += 128) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < patches; ++p) {
+        const float4 v = *reinterpret_cast<const float4*>(x + p * dim + d);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        if (local_b) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          *reinterpret_cast<uint2*>(local_b + (b * patches + p) * dim + d) = pk;
+        }
+      }
+      const float4 m = make_float4(s.x / inv, s.y / inv, s.z / inv, s.w / inv);
+      if (mean_f32) *reinterpret_cast<float4*>(mean_f32 + b * dim + d) = m;
+      if (mean_b) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(m.x, m.y), hi = __floats2bfloat162_rn(m.z, m.w);
+        *reinterpret_cast<uint2*>(mean_b + b * dim + d) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+    return;
+  }
   for (int d = lane; d < dim; d += 32) {
     float s = 0.f;
     for (int p = 0; p < patches; ++p) {
@@ -33,7 +56,7 @@ __global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, in
       s += v;
       if (local_b) local_b[(b * patches + p) * dim + d] = __float2bfloat16_rn(v);
     }
-    const float m = s / static_cast<float>(patches);
+    const float m = s / inv;
     if (mean_f32) mean_f32[b * dim + d] = m;
     if (mean_b) mean_b[b * dim + d] = __float2bfloat16_rn(m);
   }
@@ -103,6 +126,7 @@ linear_tanh_f32_kernel(const float* __restrict__ X, int64_t rows, const float* _
 }
 
 // one warp per row b: logits -> softmax over the patches -> weighted sum of the fp32 patch features -> l2norm(+1e-8)
+// HBM-bound (reads the [P, D] fp32 patch block once): float4 loads, the P softmax weights live in registers.
 __global__ void finalize_kernel(const float* __restrict__ local, int64_t rows, int patches, int dim,
                                 const float* __restrict__ partial, int n_tiles, const float* __restrict__ b_common,
                                 float* __restrict__ out) {
@@ -121,17 +145,50 @@ __global__ void finalize_kernel(const float* __restrict__ local, int64_t rows, i
   float sum = e;
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float w = e / sum;
+  float wp[kMaxPatches];
+#pragma unroll
+  for (int p = 0; p < kMaxPatches; ++p) wp[p] = __shfl_sync(0xffffffffu, w, p);
   const float* x = local + b * patches * dim;
+  float* o_row = out + b * dim;
   float ss = 0.f;
-  for (int d = lane; d < dim; d += 32) {
-    float acc = 0.f;
-    for (int p = 0; p < patches; ++p) acc = fmaf(__shfl_sync(0xffffffffu, w, p), x[p * dim + d], acc);
-    out[b * dim + d] = acc;
-    ss = fmaf(acc, acc, ss);
+  if ((dim & 3) == 0) {
+    for (int d = lane * 4; d < dim; d += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kMaxPatches; ++p) {
+        if (p < patches) {
+          const float4 v = *reinterpret_cast<const float4*>(x + p * dim + d);
+          acc.x = fmaf(wp[p], v.x, acc.x);
+          acc.y = fmaf(wp[p], v.y, acc.y);
+          acc.z = fmaf(wp[p], v.z, acc.z);
+          acc.w = fmaf(wp[p], v.w, acc.w);
+        }
+      }
+      *reinterpret_cast<float4*>(o_row + d) = acc;
+      ss = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, fmaf(acc.w, acc.w, ss))));
+    }
+  } else {
+    for (int d = lane; d < dim; d += 32) {
+      float acc = 0.f;
+#pragma unroll
+      for (int p = 0; p < kMaxPatches; ++p)
+        if (p < patches) acc = fmaf(wp[p], x[p * dim + d], acc);
+      o_row[d] = acc;
+      ss = fmaf(acc, acc, ss);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float denom = sqrtf(ss) + 1e-8f;
-  for (int d = lane; d < dim; d += 32) out[b * dim + d] = out[b * dim + d] / denom;
+  __syncwarp();
+  if ((dim & 3) == 0) {
+    for (int d = lane * 4; d < dim; d += 128) {
+      float4 v = *reinterpret_cast<float4*>(o_row + d);
+      v.x /= denom; v.y /= denom; v.z /= denom; v.w /= denom;
+      *reinterpret_cast<float4*>(o_row + d) = v;
+    }
+  } else {
+    for (int d = lane; d < dim; d += 32) o_row[d] = o_row[d] / denom;
+  }
 }
 
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
