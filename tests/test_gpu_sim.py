@@ -215,3 +215,24 @@ def test_cuda_graph_capture_of_the_tail(cuda_device):
         e_vals, e_ids, e_counts, _ = tail()
         assert torch.equal(g_ids, e_ids) and torch.equal(g_vals, e_vals) and torch.equal(g_counts, e_counts)
         assert int(g_status[0].item()) == 0
+
+
+def test_sharded_helpers_single_process(cuda_device):
+    # world_size 1 (no process group): the sharded entry points must reduce to the single-GPU calls
+    from fashionern_aaai2024_b200 import sharded
+    q, n, dim = 130, 3000, 640
+    pred, gal = unit(71, q, dim).bfloat16().to(cuda_device), unit(72, n, dim).bfloat16().to(cuda_device)
+    cls = torch.arange(n, dtype=torch.int32, device=cuda_device)
+    tgt = torch.randint(0, n, (q,), generator=torch.Generator().manual_seed(73)).int().to(cuda_device)
+    v0, i0, k0, _ = ops.sim_topk(pred, gal, 50, want_keys=True)
+    v1, i1, k1, st = sharded.sharded_topk(pred, gal, 50, 0)
+    assert torch.equal(i0, i1) and torch.equal(k0, k1) and int(st[0].item()) == 0
+    c0, r0 = ops.recall_at_k(i0, cls, tgt, (1, 10, 50))
+    c1, r1, _ = sharded.sharded_recall(pred, gal, 0, cls, tgt, (1, 10, 50))
+    assert torch.equal(c0, c1) and torch.equal(r0, r1)
+    g = torch.Generator().manual_seed(74)
+    members = torch.stack([torch.randperm(n, generator=g)[:6] for _ in range(q)]).int().to(cuda_device)
+    ref, tg = members[:, 0].contiguous(), members[:, 1].contiguous()
+    a = ops.cirr_subset_recall(pred, gal, members, ref, tg, (1, 2, 3))
+    b = sharded.sharded_cirr_subset(pred, gal, 0, members, ref, tg, (1, 2, 3))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
