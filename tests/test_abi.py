@@ -118,3 +118,21 @@ def test_header_is_plain_c_and_links(tmp_path):
     # the ctypes mirror of the largest struct must have the C layout
     import ctypes
     assert int(out[1]) == ctypes.sizeof(_lib.DvrWeights)
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_end_to_end(tmp_path, cuda_device):
+    """examples/ern_topk_demo.c: a C99 program drives ern_sim_topk with cudaMalloc'ed buffers -- no Python, no C++."""
+    import shutil
+    import subprocess
+    cuda = "/usr/local/cuda"
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("no gcc / CUDA headers")
+    exe = tmp_path / "demo"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                    os.path.join(ROOT, "examples", "ern_topk_demo.c"), "-o", str(exe), "-L", libdir, "-l:libern_b200.so",
+                    "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", f"-Wl,-rpath,{libdir}",
+                    f"-Wl,-rpath,{os.path.join(cuda, 'lib64')}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
