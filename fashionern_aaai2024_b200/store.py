@@ -130,3 +130,22 @@ class FeatureStore:
         idx = np.asarray(rows, dtype=np.int64)
         host = torch.from_numpy(np.ascontiguousarray(self._global[idx]).view(np.int16))
         return host.to(device).view(torch.bfloat16)
+
+
+def stream_topk(store: "FeatureStore", queries: torch.Tensor, k: int, *, chunk_rows: int = 1 << 22, rank: int = 0,
+                world_size: int = 1, rank_by: int = 0):
+    """Exact top-k over a gallery that does not have to fit in device memory: the rank's row block is streamed from
+    the store in ``chunk_rows`` pieces (pinned staging -> device), each piece is scored with ``ops.sim_topk`` using
+    its global ``id_offset`` and folded into the running best ``[Q,k]`` keys with ``ops.topk_merge`` -- the same
+    (value, id) wire keys and merge kernel the multi-GPU exchange uses, so the result is identical to scoring the
+    whole block at once.  Returns ``(values, ids, keys)``."""
+    from . import ops
+    begin, end = shard_bounds(store.rows, world_size, rank)
+    dev = queries.device
+    best = None
+    for s in range(begin, max(end, begin + 1), chunk_rows):
+        e = min(s + chunk_rows, end)
+        piece = store._to_device(store._global, s, e, dev, min(chunk_rows, 1 << 16))
+        _, _, keys, _ = ops.sim_topk(queries, piece, k, id_offset=s, rank_by=rank_by, want_keys=True)
+        best = keys if best is None else ops.topk_merge(torch.stack((best, keys)), k)[2]
+    return ops.topk_merge(best.unsqueeze(0), k)

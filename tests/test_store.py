@@ -58,3 +58,19 @@ def test_shard_feeds_the_scoring_kernel(tmp_path, cuda_device):
         shard, off = st.load_shard(r, 3, device=cuda_device, chunk_rows=512)
         parts.append(ops.sim_topk(pred, shard, k, id_offset=off, want_keys=True)[2])
     assert torch.equal(ops.topk_merge(torch.stack(parts), k)[2], full)
+
+
+@pytest.mark.gpu
+def test_stream_topk_equals_resident(tmp_path, cuda_device):
+    from fashionern_aaai2024_b200 import ops
+    from fashionern_aaai2024_b200.store import stream_topk
+    n, dim, k = 9001, 640, 50
+    feats = syn.features(19, n, dim, unit=True)
+    st = FeatureStore.save(str(tmp_path / "s"), feats)
+    pred = syn.features(20, 200, dim, unit=True).bfloat16().to(cuda_device)
+    want = ops.sim_topk(pred, feats.bfloat16().to(cuda_device), k, want_keys=True)
+    vals, ids, keys = stream_topk(st, pred, k, chunk_rows=2500)
+    assert torch.equal(keys, want[2]) and torch.equal(ids, want[1]) and torch.equal(vals, want[0])
+    # two "ranks" streaming their halves, merged: same answer
+    parts = [stream_topk(st, pred, k, chunk_rows=1700, rank=r, world_size=2)[2] for r in range(2)]
+    assert torch.equal(ops.topk_merge(torch.stack(parts), k)[2], want[2])
