@@ -44,6 +44,12 @@ class CombinerSimple(nn.Module):
         self._packed_versions = None
 
     # ---------------------------------------------------------------------------------------------
+    def invalidate_cache(self) -> None:
+        """Drop the packed bf16 weight copies.  They are refreshed automatically when a parameter's version counter
+        changes (``load_state_dict``, ``copy_``, optimizer steps); call this after writing through ``.data``."""
+        self._packed = None
+        self._packed_versions = None
+
     def set_mode(self, mode: str) -> "CombinerSimple":
         """'bf16' = tcgen05 tensor-core path (default); 'fp32' = FFMA validation mode (1e-5 vs the reference)."""
         if mode not in ("bf16", "fp32"):

@@ -68,6 +68,12 @@ class DVR_module(nn.Module):  # noqa: N801  (the reference's class name)
         if device is not None:
             self.to(device)
 
+    def invalidate_cache(self) -> None:
+        """Drop the packed bf16 weight copies.  They are refreshed automatically when a parameter's version counter
+        changes (``load_state_dict``, ``copy_``, optimizer steps); call this after writing through ``.data``."""
+        self._packed = None
+        self._versions = None
+
     def set_mode(self, mode: str) -> "DVR_module":
         if mode not in ("bf16", "fp32"):
             raise ErnError(f"unknown mode {mode!r}")

@@ -50,6 +50,12 @@ class VisualSR(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
+    def invalidate_cache(self) -> None:
+        """Drop the packed bf16 weight copies.  They are refreshed automatically when a parameter's version counter
+        changes (``load_state_dict``, ``copy_``, optimizer steps); call this after writing through ``.data``."""
+        self._packed = None
+        self._versions = None
+
     def set_mode(self, mode: str) -> "VisualSR":
         if mode not in ("bf16", "fp32"):
             raise ErnError(f"unknown mode {mode!r}")
