@@ -430,7 +430,7 @@ post_kernel(const float* __restrict__ X, int P, int Tn, int dim, T* __restrict__
 // ---- packed bf16 weights: per layer wq wk wv wo (DxD), wi (IxD), wo2 (DxI); then mha_in (3DxD), mha_out (DxD) --------
 static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 struct PackedLayout {
-  size_t layer_stride, wq, wk, wv, wo, wi, wo2, mha_in, mha_out, total;
+  size_t layer_stride, wq, wk, wv, wo, wi, wo2, bqkv, mha_in, mha_out, total;
 };
 static PackedLayout layout(int dim, int inter, int n_layers) {
   PackedLayout l;
@@ -441,7 +441,8 @@ static PackedLayout layout(int dim, int inter, int n_layers) {
   l.wo = 3 * al(d * d * 2);
   l.wi = 4 * al(d * d * 2);
   l.wo2 = l.wi + al(I * d * 2);
-  l.layer_stride = l.wo2 + al(d * I * 2);
+  l.bqkv = l.wo2 + al(d * I * 2);              // fp32 [3D]: query | key | value biases, for the fused QKV GEMM
+  l.layer_stride = l.bqkv + al(3 * d * 4);
   l.mha_in = l.layer_stride * n_layers;
   l.mha_out = l.mha_in + al(3 * d * d * 2);
   l.total = l.mha_out + al(d * d * 2) + 256;
@@ -464,6 +465,12 @@ int pack(const ern_dvr_weights* w, int dim, void* packed, cudaStream_t st) {
     if (!rc) rc = combiner::launch_cast_bf16(lw.wo, b + l.wo, dd, st);
     if (!rc) rc = combiner::launch_cast_bf16(lw.wi, b + l.wi, di, st);
     if (!rc) rc = combiner::launch_cast_bf16(lw.wo2, b + l.wo2, di, st);
+    if (!rc) {
+      float* bq = reinterpret_cast<float*>(b + l.bqkv);
+      ERN_CUDA(cudaMemcpyAsync(bq, lw.bq, dim * 4, cudaMemcpyDeviceToDevice, st));
+      ERN_CUDA(cudaMemcpyAsync(bq + dim, lw.bk, dim * 4, cudaMemcpyDeviceToDevice, st));
+      ERN_CUDA(cudaMemcpyAsync(bq + 2 * dim, lw.bv, dim * 4, cudaMemcpyDeviceToDevice, st));
+    }
   }
   if (!rc) rc = combiner::launch_cast_bf16(w->mha_in_w, p + l.mha_in, 3 * dd, st);
   if (!rc) rc = combiner::launch_cast_bf16(w->mha_out_w, p + l.mha_out, dd, st);
@@ -592,9 +599,16 @@ int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode,
       __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws.QKV);
       __nv_bfloat16* ctx = reinterpret_cast<__nv_bfloat16*>(ws.CTX);
       __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws.H);
-      if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wq, dim, lw.bq, qkv, 3 * dim, 0, nullptr, nullptr, sm_count, st))) return rc;
-      if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wk, dim, lw.bk, qkv, 3 * dim, dim, nullptr, nullptr, sm_count, st))) return rc;
-      if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wv, dim, lw.bv, qkv, 3 * dim, 2 * dim, nullptr, nullptr, sm_count, st))) return rc;
+      // one GEMM for Q | K | V: the three bf16 weight matrices are adjacent in the packed buffer ([3D, D]) when
+      // D*D*2 is a multiple of the 256-byte packing alignment (true for D % 128 == 0), biases are packed likewise
+      if (pl.wk == static_cast<size_t>(dim) * dim * 2) {
+        if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wq, 3 * dim, reinterpret_cast<const float*>(b + pl.bqkv),
+                                                qkv, 3 * dim, 0, nullptr, nullptr, sm_count, st))) return rc;
+      } else {
+        if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wq, dim, lw.bq, qkv, 3 * dim, 0, nullptr, nullptr, sm_count, st))) return rc;
+        if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wk, dim, lw.bk, qkv, 3 * dim, dim, nullptr, nullptr, sm_count, st))) return rc;
+        if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wv, dim, lw.bv, qkv, 3 * dim, 2 * dim, nullptr, nullptr, sm_count, st))) return rc;
+      }
       if ((rc = run_attention<__nv_bfloat16>(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ctx, dim, batch, heads, L, L, dh, st))) return rc;
       if ((rc = tc_gemm<gemmtc::kEpiResidF32>(ctx, M, dim, b + pl.wo, dim, lw.bo, nullptr, dim, 0, ws.Y, ws.X, sm_count, st))) return rc;
       layernorm_kernel<<<wb_rows, 256, 0, st>>>(ws.Y, M, dim, lw.ln1_w, lw.ln1_b, ws.X, Xb);
