@@ -147,7 +147,7 @@ def run_reference(args):
         return
     qps, t, cb = cpu_reference_qps(args, steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
     print(json.dumps({
-        "impl": "reference", "metric": "queries/sec (top-100, 640-d)", "value": qps, "unit": "queries/s",
+        "impl": "reference", "metric": f"queries/sec (top-{args.k}, {args.dim}-d)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": args.queries / qps * 1e3, "sample_pass_ms": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -343,7 +343,7 @@ def main():
             _, _, cpu_baseline = cpu_reference_qps(args)
         recall = [float(100.0 * c / Q) for c in out[2].cpu().tolist()]
         line = {
-            "metric": "queries/sec (top-100, 640-d)", "value": value, "unit": "queries/s", "n_gpus": world,
+            "metric": f"queries/sec (top-{K}, {D}-d)", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
