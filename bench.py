@@ -342,6 +342,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             _, _, cpu_baseline = cpu_reference_qps(args)
         recall = [float(100.0 * c / Q) for c in out[2].cpu().tolist()]
+        if world > 1 and sharded.exchange_in_use(args.exchange) != args.exchange:
+            args.exchange = sharded.exchange_in_use(args.exchange) + " (p2p unavailable)"
         line = {
             "metric": f"queries/sec (top-{K}, {D}-d)", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

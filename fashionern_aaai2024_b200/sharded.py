@@ -26,6 +26,11 @@ from . import ops
 from ._lib import MODE_BF16, RANK_SIMILARITY
 
 
+def exchange_in_use(requested: str) -> str:
+    """'p2p' unless setting up symmetric memory failed (then every call silently uses 'nccl')."""
+    return "nccl" if (requested == "p2p" and _p2p_error is not None) else requested
+
+
 def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
     """Rows [begin, end) owned by ``rank``: equal blocks of ceil(N/S), the last ones possibly short/empty."""
     per = (n_rows + world_size - 1) // world_size
@@ -60,6 +65,7 @@ class _PeerBuffers:
 
 
 _peer_cache = {}
+_p2p_error = None      # set when symmetric memory could not be set up: callers then use the NCCL exchange
 
 
 def _peer_buffers(nq, k, device, group) -> _PeerBuffers:
@@ -75,9 +81,17 @@ def sharded_topk(queries: torch.Tensor, local_gallery: torch.Tensor, k: int, id_
     """Global top-k of every (replicated) query over a row-sharded gallery.
     Returns ``(values [Q,k], global ids [Q,k], keys [Q,k], status int32[4])``; the first three are identical on
     every rank, ``status`` is this rank's overflow report (see ``ops.sim_topk``)."""
+    global _p2p_error
     multi = dist.is_initialized() and dist.get_world_size(group) > 1
-    if multi and exchange == "p2p":
-        pb = _peer_buffers(queries.shape[0], k, queries.device, group)
+    pb = None
+    if multi and exchange == "p2p" and _p2p_error is None:
+        try:
+            pb = _peer_buffers(queries.shape[0], k, queries.device, group)
+        except Exception as e:  # noqa: BLE001  (no P2P / symmetric-memory support on this box: NCCL path instead)
+            _p2p_error = repr(e)
+            import warnings
+            warnings.warn(f"peer-memory candidate exchange unavailable ({_p2p_error}); using the NCCL all-gather")
+    if pb is not None:
         buf, hdl = pb.bufs[pb.turn], pb.handles[pb.turn]
         pb.turn ^= 1
         status = ops.sim_topk_exchange(queries, local_gallery, k, hdl.buffer_ptrs_dev, pb.world, hdl.rank, mode=mode,
