@@ -6,6 +6,7 @@ Public surface (mirrors the reference's own, see DESIGN.md / INTEGRATION.md):
   VisualSR                                  patch attention pooling (models/fusion_model.py:97-154; 'next' row)
   compute_{fiq,shoes,200k,cirr}_val_metrics metric tails           (run/test/test_*.py, run/valid/validate_*.py)
   compute_val_metrics, score_topk_recall
+  BatchBasedClassificationLoss              training criterion      (losses/loss.py:6-14; 'next' row, fwd + bwd)
   ops.*                                     tensor-level wrappers of the C ABI (include/ern_b200.h)
   sharded.*                                 row-sharded gallery over the GPUs of one box
 
@@ -16,6 +17,7 @@ from .combiner import CombinerSimple, accelerate_ern  # noqa: F401
 from .visual_sr import VisualSR  # noqa: F401
 from .dvr import DVR_module  # noqa: F401
 from .model import ERN  # noqa: F401
+from .loss import BatchBasedClassificationLoss  # noqa: F401
 from . import ops, sharded, store  # noqa: F401
 from .metrics import (compute_200k_val_metrics, compute_cirr_val_metrics, compute_fiq_val_metrics,  # noqa: F401
                       compute_shoes_val_metrics, compute_val_metrics, score_topk_recall, set_precision,

@@ -29,6 +29,7 @@ SYMBOLS = (
     "ern_cirr_subset_recall", "ern_gather_scores", "ern_cirr_subset_from_scores",
     "ern_visualsr_packed_bytes", "ern_visualsr_pack", "ern_visualsr_workspace_bytes", "ern_visualsr_forward",
     "ern_dvr_packed_bytes", "ern_dvr_pack", "ern_dvr_workspace_bytes", "ern_dvr_encode",
+    "ern_bbc_loss_workspace_bytes", "ern_bbc_loss_forward", "ern_bbc_loss_backward",
 )
 
 
@@ -93,6 +94,10 @@ def lib() -> C.CDLL:
                                          C.POINTER(C.c_int32), i32, vp, vp, vp]
     l.ern_gather_scores.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, i64, vp, i32, vp, vp]
     l.ern_cirr_subset_from_scores.argtypes = [vp, i64, vp, i32, vp, vp, i32, C.POINTER(C.c_int32), i32, vp, vp, vp]
+    l.ern_bbc_loss_workspace_bytes.argtypes = [i64, i32, i32]
+    l.ern_bbc_loss_workspace_bytes.restype = sz
+    l.ern_bbc_loss_forward.argtypes = [vp, i64, vp, i64, i64, i32, C.c_float, i32, vp, vp, vp, sz, vp]
+    l.ern_bbc_loss_backward.argtypes = [vp, i64, vp, i64, i64, i32, C.c_float, i32, vp, vp, vp, i64, vp, i64, vp, sz, vp]
     l.ern_visualsr_packed_bytes.argtypes = [i32]
     l.ern_visualsr_packed_bytes.restype = sz
     l.ern_visualsr_pack.argtypes = [C.POINTER(VisualSRWeights), i32, vp, vp]

@@ -504,4 +504,56 @@ int ern_cirr_subset_from_scores(const float* scores_dev, int64_t nq, const int32
                           rank_dev, static_cast<cudaStream_t>(stream));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+size_t ern_bbc_loss_workspace_bytes(int64_t batch, int dim, int mode) {
+  if (batch < 0 || dim <= 0) return 0;
+  return bbcloss::workspace_bytes(batch, dim, mode);
+}
+
+static int bbc_check(const float* pred, int64_t ldp, const float* tar, int64_t ldt, int64_t batch, int dim, int mode,
+                     const void* workspace, size_t workspace_bytes) {
+  ERN_REQUIRE(pred && tar && batch >= 1 && dim > 0 && ldp >= dim && ldt >= dim, "bad arguments");
+  ERN_REQUIRE(batch <= (1 << 20), "batch too large (%lld)", (long long)batch);
+  if (mode != ERN_MODE_BF16 && mode != ERN_MODE_FP32) {
+    set_error("unknown mode %d", mode);
+    return ERN_ERR_ARG;
+  }
+  if (mode == ERN_MODE_BF16 && dim % 64 != 0) {
+    set_error("bf16 loss needs dim %% 64 == 0 (got %d)", dim);
+    return ERN_ERR_UNSUPPORTED;
+  }
+  const size_t need = bbcloss::workspace_bytes(batch, dim, mode);
+  if (workspace_bytes < need || !workspace) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return ERN_ERR_WORKSPACE;
+  }
+  return ERN_OK;
+}
+
+int ern_bbc_loss_forward(const float* pred_dev, int64_t ldp, const float* tar_dev, int64_t ldt, int64_t batch, int dim,
+                         float scale, int mode, float* loss_dev, float* lse_dev, void* workspace_dev,
+                         size_t workspace_bytes, void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  if ((rc = bbc_check(pred_dev, ldp, tar_dev, ldt, batch, dim, mode, workspace_dev, workspace_bytes))) return rc;
+  ERN_REQUIRE(loss_dev, "loss output is required");
+  return bbcloss::forward(pred_dev, ldp, tar_dev, ldt, batch, dim, scale, mode, loss_dev, lse_dev, workspace_dev,
+                          di.sm_count, static_cast<cudaStream_t>(stream));
+}
+
+int ern_bbc_loss_backward(const float* pred_dev, int64_t ldp, const float* tar_dev, int64_t ldt, int64_t batch, int dim,
+                          float scale, int mode, const float* lse_dev, const float* grad_out_dev, float* dpred_dev,
+                          int64_t lddp, float* dtar_dev, int64_t lddt, void* workspace_dev, size_t workspace_bytes,
+                          void* stream) {
+  DeviceInfo di;
+  int rc = current_device(&di);
+  if (rc) return rc;
+  if ((rc = bbc_check(pred_dev, ldp, tar_dev, ldt, batch, dim, mode, workspace_dev, workspace_bytes))) return rc;
+  ERN_REQUIRE(lse_dev && dpred_dev && dtar_dev, "lse and both gradient outputs are required");
+  ERN_REQUIRE(lddp >= dim && lddt >= dim && lddp % 4 == 0 && lddt % 4 == 0, "gradient row strides must be >= dim and multiples of 4");
+  return bbcloss::backward(pred_dev, ldp, tar_dev, ldt, batch, dim, scale, mode, lse_dev, grad_out_dev, dpred_dev, lddp,
+                           dtar_dev, lddt, workspace_dev, di.sm_count, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -15,7 +15,7 @@ template <int kAct>
 __global__ void __launch_bounds__(kThreads)
 linear_f32_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, const float* __restrict__ W, int K, int N,
                   const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ out,
-                  int64_t ldo) {
+                  int64_t ldo, int64_t ldw) {
   __shared__ float xs[kKc][kTile + 1];
   __shared__ float ws[kKc][kTile + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -27,7 +27,7 @@ linear_f32_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, const 
       const int r = e / kKc, kk = e % kKc;
       const bool kin = (k0 + kk) < K;
       xs[kk][r] = (kin && r0 + r < rows) ? X[(r0 + r) * ldx + k0 + kk] : 0.f;
-      ws[kk][r] = (kin && n0 + r < N) ? W[static_cast<int64_t>(n0 + r) * K + k0 + kk] : 0.f;
+      ws[kk][r] = (kin && n0 + r < N) ? W[static_cast<int64_t>(n0 + r) * ldw + k0 + kk] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -63,13 +63,14 @@ linear_f32_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, const 
 // rows may exceed 65535 * 64: the row dimension is walked in slabs
 template <int kAct>
 static int launch(const float* X, int64_t ldx, int64_t rows, const float* W, int K, int N, const float* bias,
-                  const float* residual, float* out, int64_t ldo, cudaStream_t st) {
+                  const float* residual, float* out, int64_t ldo, cudaStream_t st, int64_t ldw = 0) {
+  if (ldw == 0) ldw = K;
   const int64_t slab = 65535ll * kTile;
   for (int64_t s = 0; s < rows; s += slab) {
     const int64_t r = rows - s < slab ? rows - s : slab;
     dim3 grid(cdiv(N, kTile), cdiv(r, kTile));
     linear_f32_kernel<kAct><<<grid, kThreads, 0, st>>>(X + s * ldx, ldx, r, W, K, N, bias,
-                                                      residual ? residual + s * ldo : nullptr, out + s * ldo, ldo);
+                                                      residual ? residual + s * ldo : nullptr, out + s * ldo, ldo, ldw);
   }
   ERN_CUDA(cudaGetLastError());
   return ERN_OK;

@@ -23,6 +23,10 @@ enum Epilogue {
   kEpiBiasBf16 = 4,   // out_bf16[r, col0 + n] = bf16(acc + bias[n])
   kEpiGeluBf16 = 5,   // out_bf16[r, col0 + n] = bf16(gelu_erf(acc + bias[n]))
   kEpiResidF32 = 6,   // out_f32[r, n] = acc + bias[n] + (residual ? residual[r, n] : 0)
+  // in-batch classification loss (losses/loss.py:10-14), logits x[r, n] = alpha * acc:
+  kEpiLse = 7,        // partial[tile, r] = max_n x, partial2[tile, r] = sum_n exp(x - max); diag[r] = x[r, r]
+  kEpiSmGradRow = 8,  // out_bf16[r, n] = bf16((exp(x - rowvec[r]) - [r == n]) * beta * gscale[0]), 0 for n >= N
+  kEpiSmGradCol = 9,  // out_bf16[r, n] = bf16((exp(x - bias[n])   - [r == n]) * beta * gscale[0]), 0 for n >= N
 };
 
 constexpr int kBlockM = 128;
@@ -49,6 +53,11 @@ struct Params {
   const float* cvec;    // [M / P, N]         kEpiSrLocal
   int patches;          // P
   const float* residual;  // [M, ldo] fp32     kEpiResidF32 (nullable)
+  float alpha, beta;      // kEpiLse / kEpiSmGrad*: logit scale, gradient coefficient
+  float* partial2;        // [N / kBlockN, M]   kEpiLse (partial has the same layout there)
+  float* diag;            // [M]                kEpiLse
+  const float* rowvec;    // [M]                kEpiSmGradRow: per-row logsumexp
+  const float* gscale;    // [1] device scalar multiplied into beta (upstream gradient), nullable
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -67,6 +76,12 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_abs = 1.0f - poly * t * __expf(-z * z);
   const float erf_x = copysignf(erf_abs, x);
   return 0.5f * x * (1.0f + erf_x);
+}
+// e^x for the loss epilogues: one FMUL + MUFU.EX2 (flush-to-zero form: no denormal pre-scaling selects)
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -200,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float* sshift = sscale + kBlockN;
       for (int i = epi_tid; i < kBlockN; i += 128) {
         const bool in = n0 + i < p.n;
-        sbias[i] = in ? p.bias[n0 + i] : 0.f;
+        sbias[i] = (in && p.bias) ? p.bias[n0 + i] : 0.f;
         if (kEpi == kEpiGate || kEpi == kEpiSrGlobal) swg[i] = in ? p.wg[n0 + i] : 0.f;
         if (kEpi == kEpiSrGlobal) {
           sscale[i] = in ? p.scale[n0 + i] : 0.f;
@@ -231,7 +246,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint8_t* stg = stage_smem + (warp - 2) * kStgWarpBytes;
       const int64_t row_base = static_cast<int64_t>(m0) + quad * 32;
       const int srow = lane >> 3, spiece = lane & 7;
-      if (kEpi == kEpiStoreRelu || kEpi == kEpiBiasBf16 || kEpi == kEpiGeluBf16) {
+      constexpr bool kSmGrad = kEpi == kEpiSmGradRow || kEpi == kEpiSmGradCol;
+      float row_lse = 0.f, coef = 0.f;
+      if (kSmGrad) {
+        coef = p.beta * (p.gscale ? p.gscale[0] : 1.f);
+        if (kEpi == kEpiSmGradRow && row_ok) row_lse = p.rowvec[row];
+      }
+      float run_max = -INFINITY, run_sum = 0.f, diag_val = 0.f;   // kEpiLse
+      if (kEpi == kEpiStoreRelu || kEpi == kEpiBiasBf16 || kEpi == kEpiGeluBf16 || kSmGrad) {
 #pragma unroll 1
         for (int g = 0; g < kBlockN / 64; ++g) {
           if (n0 + g * 64 >= p.n) break;     // ragged last column tile: nothing more to emit
@@ -240,11 +262,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::tmem_ld_32x32(taddr + g * 64 + 32, hi);
           ptx::tmem_ld_wait();
           uint32_t packed[32];
+          // kSmGrad: position of this row's diagonal element / number of real columns, relative to this group
+          const int64_t dj64 = row - n0 - g * 64;
+          const int dj = (dj64 >= 0 && dj64 < 64) ? static_cast<int>(dj64) : -1;
+          const int valid = p.n - n0 - g * 64;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int cidx = g * 64 + 2 * j;
-            float x0 = __uint_as_float(j < 16 ? lo[2 * j] : hi[2 * j - 32]) + sbias[cidx];
-            float x1 = __uint_as_float(j < 16 ? lo[2 * j + 1] : hi[2 * j - 31]) + sbias[cidx + 1];
+            float x0 = __uint_as_float(j < 16 ? lo[2 * j] : hi[2 * j - 32]);
+            float x1 = __uint_as_float(j < 16 ? lo[2 * j + 1] : hi[2 * j - 31]);
+            if (kSmGrad) {
+              // The logit is rounded exactly as in the forward pass (no fma contraction), so that exp(x - lse) is
+              // consistent with the lse it was reduced into (a 1-row batch gives a gradient of exactly 0).
+              // Diagonal and ragged-column handling are selects, not branches (a ternary around __expf compiled to
+              // 86 divergent BSSY/BSYNC regions per 64 columns and made this epilogue 3x slower than the MMAs).
+              const float l0 = kEpi == kEpiSmGradRow ? row_lse : sbias[cidx];
+              const float l1 = kEpi == kEpiSmGradRow ? row_lse : sbias[cidx + 1];
+              float e0 = exp_fast(__fmul_rn(p.alpha, x0) - l0);
+              float e1 = exp_fast(__fmul_rn(p.alpha, x1) - l1);
+              e0 = (2 * j == dj) ? e0 - 1.f : e0;
+              e1 = (2 * j + 1 == dj) ? e1 - 1.f : e1;
+              x0 = (2 * j < valid) ? e0 * coef : 0.f;
+              x1 = (2 * j + 1 < valid) ? e1 * coef : 0.f;
+            } else {
+              x0 += sbias[cidx];
+              x1 += sbias[cidx + 1];
+            }
             if (kEpi == kEpiStoreRelu) {
               x0 = fmaxf(x0, 0.f);
               x1 = fmaxf(x1, 0.f);
@@ -274,7 +317,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t cur[32];
           ptx::tmem_ld_32x32(taddr + c * 32, cur);
           ptx::tmem_ld_wait();
-          if (kEpi == kEpiGate) {
+          if (kEpi == kEpiLse) {
+            // online logsumexp over this tile's columns; columns >= N (ragged last tile) are skipped
+            const int valid = p.n - (n0 + c * 32);
+            const int dj = static_cast<int>(row - (n0 + c * 32));
+            float x[32];
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              x[j] = j < valid ? __fmul_rn(p.alpha, __uint_as_float(cur[j])) : -INFINITY;
+              cmax = fmaxf(cmax, x[j]);
+              if (j == dj) diag_val = x[j];
+            }
+            const float new_max = fmaxf(run_max, cmax);
+            float csum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) csum += exp_fast(x[j] - new_max);
+            run_sum = run_sum * exp_fast(run_max - new_max) + csum;
+            run_max = new_max;
+          } else if (kEpi == kEpiGate) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float h = fmaxf(__uint_as_float(cur[j]) + sbias[c * 32 + j], 0.f);
@@ -346,6 +407,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       if ((kEpi == kEpiGate || kEpi == kEpiSrLocal) && row_ok) p.partial[row * n_tiles + nt] = dot;
+      if (kEpi == kEpiLse && row_ok) {
+        p.partial[nt * p.m + row] = run_max;      // [tile, M]: consecutive lanes own consecutive rows
+        p.partial2[nt * p.m + row] = run_sum;
+        if (row >= n0 && row < n0 + kBlockN && row < p.n) p.diag[row] = diag_val;
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {

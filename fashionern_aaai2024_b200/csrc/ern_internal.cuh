@@ -63,6 +63,14 @@ int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode,
            const float* tokens, int64_t batch, float* out_cross, float* out_seq_mean, void* workspace, int sm_count,
            cudaStream_t st);
 }
+namespace bbcloss {
+size_t workspace_bytes(int64_t b, int dim, int mode);
+int forward(const float* pred, int64_t ldp, const float* tar, int64_t ldt, int64_t b, int dim, float scale, int mode,
+            float* loss, float* lse, void* workspace, int sm_count, cudaStream_t st);
+int backward(const float* pred, int64_t ldp, const float* tar, int64_t ldt, int64_t b, int dim, float scale, int mode,
+             const float* lse, const float* grad_out, float* dpred, int64_t lddp, float* dtar, int64_t lddt,
+             void* workspace, int sm_count, cudaStream_t st);
+}
 namespace visualsr {
 size_t packed_bytes(int dim);
 int pack(const ern_visualsr_weights* w, int dim, void* packed, cudaStream_t st);

@@ -261,3 +261,55 @@ def cirr_subset_from_scores(scores: torch.Tensor, members: torch.Tensor, referen
                                                     ranks.data_ptr(), L.stream_ptr(dev)))
     launch_counter.add(2 if nq else 1)
     return counts, ranks
+
+
+def bbc_loss_forward(pred: torch.Tensor, tar: torch.Tensor, scale: float = 100.0, mode: int = MODE_BF16
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """In-batch classification loss (losses/loss.py:10-14): mean cross entropy of ``scale * pred @ tar.T`` against
+    ``arange(B)``.  Returns (loss [1] fp32, row logsumexp [B] fp32)."""
+    p = _rowmajor(pred, "pred")
+    t = _rowmajor(tar, "tar")
+    if p.dtype != torch.float32 or t.dtype != torch.float32 or p.shape != t.shape:
+        raise ErnError("pred / tar must be float32 tensors of the same [B, D] shape")
+    b, d = p.shape
+    loss = torch.empty(1, dtype=torch.float32, device=p.device)
+    lse = torch.empty(b, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        nbytes = L.lib().ern_bbc_loss_workspace_bytes(b, d, mode)
+        ws = _workspace(nbytes, p.device)
+        L.check(L.lib().ern_bbc_loss_forward(p.data_ptr(), p.stride(0), t.data_ptr(), t.stride(0), b, d, float(scale),
+                                             mode, loss.data_ptr(), lse.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             L.stream_ptr(p.device)))
+    launch_counter.add(4 if mode == MODE_BF16 else 3)     # cast, GEMM+lse, combine, mean | GEMM, row lse, mean
+    return loss, lse
+
+
+def bbc_loss_backward(pred: torch.Tensor, tar: torch.Tensor, lse: torch.Tensor, grad_out: Optional[torch.Tensor] = None,
+                      scale: float = 100.0, mode: int = MODE_BF16) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gradient of :func:`bbc_loss_forward` with respect to ``pred`` and ``tar`` (both [B, D] fp32), multiplied by the
+    device scalar ``grad_out`` (the upstream gradient, e.g. a GradScaler factor) when given."""
+    p = _rowmajor(pred, "pred")
+    t = _rowmajor(tar, "tar")
+    L.require_cuda(lse, "lse")
+    if p.dtype != torch.float32 or t.dtype != torch.float32 or p.shape != t.shape:
+        raise ErnError("pred / tar must be float32 tensors of the same [B, D] shape")
+    b, d = p.shape
+    lse = lse.float().contiguous()
+    if lse.numel() != b:
+        raise ErnError("lse must hold one value per row")
+    g_ptr = None
+    if grad_out is not None:
+        L.require_cuda(grad_out, "grad_out")
+        grad_out = grad_out.reshape(-1).float().contiguous()
+        g_ptr = grad_out.data_ptr()
+    dpred = torch.empty((b, d), dtype=torch.float32, device=p.device)
+    dtar = torch.empty((b, d), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        nbytes = L.lib().ern_bbc_loss_workspace_bytes(b, d, mode)
+        ws = _workspace(nbytes, p.device)
+        L.check(L.lib().ern_bbc_loss_backward(p.data_ptr(), p.stride(0), t.data_ptr(), t.stride(0), b, d, float(scale),
+                                              mode, lse.data_ptr(), g_ptr, dpred.data_ptr(), dpred.stride(0),
+                                              dtar.data_ptr(), dtar.stride(0), ws.data_ptr(), ws.numel(),
+                                              L.stream_ptr(p.device)))
+    launch_counter.add(5 if mode == MODE_BF16 else 6)     # cast+transpose, 2 softmax-gradient GEMMs, 2 GEMMs
+    return dpred, dtar

@@ -9,7 +9,7 @@ sides see bit-identical inputs.  Shapes follow SURVEY.md section 8(d).
 from __future__ import annotations
 
 import hashlib
-from typing import Dict, List
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch
@@ -145,6 +145,18 @@ def features(seed: int, rows: int, dim: int, unit: bool = False) -> torch.Tensor
     if unit:
         x = torch.nn.functional.normalize(x, dim=-1)
     return x
+
+
+def loss_pair(seed: int, rows: int, dim: int, spread: float = 0.25, noise: float = 0.25
+              ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(predicted, target) unit-norm features of one training batch.  Targets share a common direction (pairwise
+    cosine ~0.94, like CLIP embeddings of one product category) and row i of ``predicted`` is a noisy copy of target
+    i (cosine ~0.97), so the 100x-scaled in-batch classification loss (losses/loss.py:10-14) is neither saturated
+    nor at chance."""
+    common = features(seed + 2, 1, dim, unit=True)
+    tar = torch.nn.functional.normalize(common + spread * features(seed, rows, dim, unit=True), dim=-1)
+    pred = torch.nn.functional.normalize(tar + noise * features(seed + 1, rows, dim, unit=True), dim=-1)
+    return pred, tar
 
 
 def patch_features(seed: int, rows: int, dim: int, patches: int = PATCHES) -> torch.Tensor:

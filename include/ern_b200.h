@@ -267,6 +267,27 @@ ERN_API int ern_cirr_subset_from_scores(const float* scores_dev, int64_t nq, con
                                 int rank_by, const int32_t* ks, int nk, int32_t* counts_dev,
                                 int32_t* rank_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * In-batch classification loss.  Replaces BatchBasedClassificationLoss.forward
+ * (losses/loss.py:10-14): logits = scale * pred . tar^T (scale = 100, :11), labels = arange(batch) (:12),
+ * loss = mean cross entropy (:14) -- and its gradient (what autograd derives for run/train/train_fiq.py:134-137).
+ *   pred, tar   [batch, dim] fp32, row strides ldp / ldt (elements); dim % 64 == 0, batch >= 1
+ *   mode        ERN_MODE_BF16: tcgen05 GEMMs with a logsumexp / softmax-gradient epilogue, operands rounded to
+ *               bf16, logits never stored;  ERN_MODE_FP32: validation path, fp32 FFMA
+ *   loss_dev    [1] fp32;  lse_dev [batch] fp32 row logsumexp (nullable in forward; required by backward)
+ *   backward:   grad_out_dev [1] fp32 device scalar = d(objective)/d(loss) (nullable = 1; a GradScaler factor
+ *               arrives here), dpred / dtar [batch, dim] fp32 with row strides lddp / lddt (multiples of 4)
+ * Workspace: ern_bbc_loss_workspace_bytes(batch, dim, mode) bytes, contents need not survive between the calls.
+ * ------------------------------------------------------------------------------------------- */
+ERN_API size_t ern_bbc_loss_workspace_bytes(int64_t batch, int dim, int mode);
+ERN_API int ern_bbc_loss_forward(const float* pred_dev, int64_t ldp, const float* tar_dev, int64_t ldt,
+                                 int64_t batch, int dim, float scale, int mode, float* loss_dev, float* lse_dev,
+                                 void* workspace_dev, size_t workspace_bytes, void* stream);
+ERN_API int ern_bbc_loss_backward(const float* pred_dev, int64_t ldp, const float* tar_dev, int64_t ldt,
+                                  int64_t batch, int dim, float scale, int mode, const float* lse_dev,
+                                  const float* grad_out_dev, float* dpred_dev, int64_t lddp, float* dtar_dev,
+                                  int64_t lddt, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

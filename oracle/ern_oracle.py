@@ -26,6 +26,25 @@ import torch.nn.functional as F
 
 
 # --------------------------------------------------------------------------------------
+# Training criterion
+# --------------------------------------------------------------------------------------
+def bbc_loss(predicted_features: torch.Tensor, tar_features: torch.Tensor, scale: float = 100.0):
+    """``BatchBasedClassificationLoss.forward`` (losses/loss.py:10-14) and the gradient autograd derives for it,
+    written out explicitly in float64: logits = scale * P @ T.T (:11), labels = arange(B) (:12), mean cross entropy
+    (:14);  dlogits = (softmax - I) / B, dP = scale * dlogits @ T, dT = scale * dlogits.T @ P.
+    Returns (loss float, row logsumexp [B], dP [B,D], dT [B,D]) as float64 numpy."""
+    p = predicted_features.detach().double().numpy()
+    t = tar_features.detach().double().numpy()
+    b = p.shape[0]
+    x = scale * (p @ t.T)
+    m = x.max(axis=1, keepdims=True)
+    lse = (m + np.log(np.exp(x - m).sum(axis=1, keepdims=True)))[:, 0]
+    loss = float(np.mean(lse - np.diag(x)))
+    dx = (np.exp(x - lse[:, None]) - np.eye(b)) / b
+    return loss, lse, scale * (dx @ t), scale * (dx.T @ p)
+
+
+# --------------------------------------------------------------------------------------
 # Fusion head
 # --------------------------------------------------------------------------------------
 def combiner_forward(sd: Dict[str, torch.Tensor], image_features: torch.Tensor,

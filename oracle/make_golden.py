@@ -233,6 +233,27 @@ def make_visualsr_golden(dim, rows, seed):
     return {"dim": dim, "rows": rows, "seed": seed}
 
 
+def make_loss_golden(dim, rows, seed):
+    """Reference ``BatchBasedClassificationLoss`` (losses/loss.py) + torch autograd vs the explicit restatement."""
+    ref.install()
+    from losses.loss import BatchBasedClassificationLoss
+    pred, tar = syn.loss_pair(seed, rows, dim)
+    p = pred.clone().requires_grad_(True)
+    t = tar.clone().requires_grad_(True)
+    loss = BatchBasedClassificationLoss()(p, t)
+    loss.backward()
+    mine, _, dp, dt = orc.bbc_loss(pred, tar)
+    err_l = abs(mine - float(loss)) / abs(float(loss))
+    err_g = max(float(np.abs(dp - p.grad.numpy()).max()), float(np.abs(dt - t.grad.numpy()).max()))
+    assert err_l < 2e-6 and err_g < 2e-6, (err_l, err_g)
+    np.savez(os.path.join(GOLDEN, f"bbcloss{dim}.npz"), loss=np.float32(float(loss)), dpred=p.grad.numpy(),
+             dtar=t.grad.numpy(),
+             meta=np.array(json.dumps({"dim": dim, "rows": rows, "seed": seed, "rel_err_loss_restatement": err_l,
+                                       "max_abs_err_grad_restatement": err_g})))
+    return {"dim": dim, "rows": rows, "seed": seed, "loss": float(loss), "rel_err_loss_restatement": err_l,
+            "max_abs_err_grad_restatement": err_g}
+
+
 def make_dvr_golden(dim, rows, seed):
     """Reference ``DVR_module`` (BERT + MHA + VisualSR + 3 heads) verbatim vs the explicit restatement."""
     ref.install()
@@ -297,10 +318,21 @@ def main():
     ap.add_argument("--no-full", action="store_true")
     ap.add_argument("--only-full", action="store_true", help="keep the committed fixtures, redo the full-size pins")
     ap.add_argument("--only-visualsr", action="store_true", help="only (re)make the VisualSR fixtures")
+    ap.add_argument("--only-loss", action="store_true", help="only (re)make the training-criterion fixtures")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    loss_cases = [make_loss_golden(640, 48, 700), make_loss_golden(512, 100, 710)]
+    if args.only_loss:
+        with open(os.path.join(GOLDEN, "pin_report.json")) as f:
+            old = json.load(f)
+        old["bbc_loss"] = loss_cases
+        with open(os.path.join(GOLDEN, "pin_report.json"), "w") as f:
+            json.dump(old, f, indent=1)
+        print(loss_cases)
+        return
     report = {"torch": torch.__version__, "numpy": np.__version__, "cases": {}, "full": {}}
+    report["bbc_loss"] = loss_cases
     report["visualsr"] = [make_visualsr_golden(640, 40, 300), make_visualsr_golden(512, 40, 400)]
     report["dvr"] = [make_dvr_golden(640, 6, 500), make_dvr_golden(512, 6, 600)]
     report["full_model"] = [make_full_model_golden("ernfull_fiq640", "fiq", 640, 40, 160, 1300),

@@ -115,3 +115,20 @@ def test_dvr_restatement_matches_reference(dim):
     assert float((out - torch.from_numpy(z["out"])).abs().max()) < 2e-6
     assert float((hidden[:, 0] - torch.from_numpy(z["hidden_cls"])).abs().max()) < 2e-5
     assert float((hidden[:, -1] - torch.from_numpy(z["hidden_last"])).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("dim", [640, 512])
+def test_loss_restatement_matches_reference(dim):
+    # reference BatchBasedClassificationLoss + torch autograd (losses/loss.py:10-14) vs the explicit float64 formulas
+    z, meta = load_golden(f"bbcloss{dim}")
+    pred, tar = syn.loss_pair(meta["seed"], meta["rows"], dim)
+    loss, lse, dp, dt = orc.bbc_loss(pred, tar)
+    assert abs(loss - float(z["loss"])) <= 5e-6 * abs(float(z["loss"]))
+    assert 0.05 < loss < 2.0                                  # neither saturated nor at chance (log B)
+    assert float(np.abs(dp - z["dpred"]).max()) < 5e-6 and float(np.abs(dt - z["dtar"]).max()) < 5e-6
+    # gradient of a mean of cross entropies: every column of dlogits sums to a known value -> sum_i dT rows
+    eps = 1e-3
+    d = torch.zeros_like(pred)
+    d[3, 5] = eps
+    num = (orc.bbc_loss(pred + d, tar)[0] - orc.bbc_loss(pred - d, tar)[0]) / (2 * eps)
+    assert abs(num - dp[3, 5]) < 1e-6 + 1e-4 * abs(dp[3, 5])
