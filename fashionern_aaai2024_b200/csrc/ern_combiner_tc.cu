@@ -5,10 +5,10 @@
 //                                                          (this replaces torch.cat, :90)
 //   kGate  : C is multiplied by w2 and row-reduced       -> per 256-column tile partial of the gate logit;
 //                                                          h[B,8D] (:74-75) never reaches HBM
-// A [M,K] and W [N,K] are bf16, K-major, fed by TMA into a 4-stage ring of 128x64 / 256x64 swizzled tiles;
-// the 128 x 256 fp32 accumulator is double buffered in TMEM (512 columns) so the epilogue of tile i overlaps
-// the MMAs of tile i+1.  The finaliser (gate sigmoid, blend from the fp32 inputs, L2-normalise) is shared
-// with the fp32 path.
+// A [M,K] and W [N,K] are bf16, K-major, fed by TMA into a 6-stage ring of 128-row x 64 swizzled tiles per CTA;
+// a CTA pair issues 256 x 256 x 16 cta_group::2 MMAs, the fp32 accumulator (256 TMEM columns per CTA) is double
+// buffered (512 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.  The finaliser (gate sigmoid,
+// blend from the fp32 inputs, L2-normalise) is shared with the fp32 path.
 #include "ern_gemm_tc.cuh"
 
 namespace ern {
