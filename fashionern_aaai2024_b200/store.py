@@ -74,6 +74,47 @@ class FeatureStore:
             json.dump({"rows": rows, "dim": dim, "patches": patches, "dtype": "bf16", "version": VERSION}, f)
         return FeatureStore(path)
 
+    @staticmethod
+    def import_patch_dir(path: str, patch_dir: str, names: Sequence[str], features: torch.Tensor,
+                         pattern: str = "{}.pth", workers: int = 8, chunk_rows: int = 4096) -> "FeatureStore":
+        """Pack the reference's on-disk patch features -- one ``torch.save``d ``[P, D]`` tensor per image at
+        ``<patch_dir>/<name>.pth`` (dataloader/fashioniq.py:69-70,97-98: ``fashion-iq/fashion_local13/``;
+        dataloader/cirr.py:55-56,85-86: ``cirr_dataset/cirr_local_13/``) -- together with the ``[N, D]`` global features
+        of the same images into one store.  Files are read by a thread pool and written in row chunks, so the
+        ``[N, P, D]`` tensor never has to exist in host memory."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        rows, dim = features.shape
+        if len(names) != rows:
+            raise ValueError("names must have one entry per row")
+        os.makedirs(path, exist_ok=True)
+
+        def read(name: str) -> torch.Tensor:
+            t = torch.load(os.path.join(patch_dir, pattern.format(name)), map_location="cpu")
+            t = t.reshape(-1, t.shape[-1]).float()
+            if t.shape[1] != dim:
+                raise ValueError(f"{name}: patch feature dim {t.shape[1]} != {dim}")
+            return t
+
+        patches = int(read(names[0]).shape[0]) if rows else 0
+        with ThreadPoolExecutor(max_workers=max(1, workers)) as pool, \
+                open(os.path.join(path, "local.bf16"), "wb") as f:
+            for s in range(0, rows, chunk_rows):
+                block = list(pool.map(read, names[s:s + chunk_rows]))
+                for nm, t in zip(names[s:s + chunk_rows], block):
+                    if t.shape[0] != patches:
+                        raise ValueError(f"{nm}: {t.shape[0]} patches, expected {patches}")
+                f.write(_as_bf16_bits(torch.stack(block)).tobytes())
+        with open(os.path.join(path, "global.bf16"), "wb") as f:
+            for s in range(0, rows, 1 << 18):
+                f.write(_as_bf16_bits(features[s:s + (1 << 18)]).tobytes())
+        with open(os.path.join(path, "names.txt"), "w") as f:
+            for nm in names:
+                f.write(str(nm).replace("\n", " ") + "\n")
+        with open(os.path.join(path, "meta.json"), "w") as f:
+            json.dump({"rows": rows, "dim": dim, "patches": patches, "dtype": "bf16", "version": VERSION}, f)
+        return FeatureStore(path)
+
     # ------------------------------------------------------------------------------------------------
     @property
     def names(self) -> List[str]:

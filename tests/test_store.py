@@ -45,6 +45,28 @@ def test_empty_and_bad_store(tmp_path):
         FeatureStore.save(str(tmp_path / "b"), torch.zeros(3, 8), names=["a"])
 
 
+def test_import_of_the_reference_per_image_patch_files(tmp_path):
+    # the reference keeps one torch.save()d [13, D] tensor per image (dataloader/fashioniq.py:69-70, cirr.py:55-56)
+    n, dim = 37, 64
+    feats = syn.features(4, n, dim)
+    local = syn.patch_features(5, n, dim)
+    names = syn.unique_names(n)
+    src = tmp_path / "fashion_local13"
+    src.mkdir()
+    for i, nm in enumerate(names):
+        torch.save(local[i] if i % 2 else local[i][None], str(src / f"{nm}.pth"))       # [13,D] and [1,13,D] both occur
+    st = FeatureStore.import_patch_dir(str(tmp_path / "packed"), str(src), names, feats, workers=3, chunk_rows=10)
+    assert (st.rows, st.dim, st.patches) == (n, dim, 13) and st.names == names
+    rows = [36, 0, 7]
+    assert torch.equal(st.load_local(rows, device="cpu"), local.bfloat16()[rows])
+    assert torch.equal(st.gather(rows, device="cpu"), feats.bfloat16()[rows])
+    with pytest.raises(FileNotFoundError):
+        FeatureStore.import_patch_dir(str(tmp_path / "bad"), str(src), names + ["missing"], torch.zeros(n + 1, dim))
+    torch.save(torch.zeros(5, dim), str(src / "short.pth"))
+    with pytest.raises(ValueError):
+        FeatureStore.import_patch_dir(str(tmp_path / "bad2"), str(src), names + ["short"], torch.zeros(n + 1, dim))
+
+
 @pytest.mark.gpu
 def test_shard_feeds_the_scoring_kernel(tmp_path, cuda_device):
     from fashionern_aaai2024_b200 import ops
