@@ -64,18 +64,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-// erf-GELU for the bf16 path: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 rounding of
-// the stored activation) -- ~4x fewer instructions than erff in an epilogue that otherwise paces the GEMM
+// erf-GELU for the bf16 path.  gelu(x) = x * Phi(x) = max(x, 0) - |x| * h with h = erfc(|x| / sqrt 2) / 2, and
+// erfc(z) = 2^(z * P(z)) with a degree-4 minimax P (fitted on [0, 4.2], monotone beyond; |gelu error| < 1.2e-6 for
+// all x, far below the bf16 rounding of the stored activation).  11 issue slots and ONE MUFU per element: the
+// Abramowitz-Stegun form used before (rcp + ex2 = two MUFU ops, ~21 instructions) made the FFN-1 epilogue
+// MUFU-bound at 2.5x the duration of its MMAs.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  const float erf_x = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_x);
+  float p = fmaf(-0.00294416647f, z, 0.0295900748f);
+  p = fmaf(p, z, -0.14866567f);
+  p = fmaf(p, z, -0.918509346f);
+  p = fmaf(p, z, -1.62788901f);
+  p = fmaf(p, z, -1.0f);                         // log2(erfc(z) / 2)
+  float h;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(p));
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
 // e^x for the loss epilogues: one FMUL + MUFU.EX2 (flush-to-zero form: no denormal pre-scaling selects)
 __device__ __forceinline__ float exp_fast(float x) {
@@ -152,7 +155,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t stage = 0, phase = 0;
       for (int t = unit; t < total; t += n_units) {
         const int m0 = (t / n_tiles) * (kBlockM * kCta) + rank * kBlockM;
-        const int n0 = (t % n_tiles) * kBlockN + rank * kBRows;
+        // ragged last column tile with at most kBlockN / 2 real columns: the MMA warp issues half-width MMAs for it,
+        // which read the first kBRows / 2 rows of each CTA's W tile -- so CTA 1's rows start kBRows / 2 further on
+        const int nt0 = (t % n_tiles) * kBlockN;
+        const bool narrow = kPair && nt0 + kBlockN / 2 >= p.n;
+        const int n0 = nt0 + rank * (narrow ? kBRows / 2 : kBRows);
         for (int kb = 0; kb < kblocks; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[stage]), phase ^ 1, nullptr, 11);
           const uint32_t full = ptx::smem_u32(&full_bar[stage]);
@@ -177,9 +184,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockM * kCta, kBlockN);
+      constexpr uint32_t idesc_full = ptx::idesc_bf16_f32(kBlockM * kCta, kBlockN);
+      constexpr uint32_t idesc_half = ptx::idesc_bf16_f32(kBlockM * kCta, kBlockN / 2);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = unit; t < total; t += n_units) {
+        const bool narrow = kPair && (t % n_tiles) * kBlockN + kBlockN / 2 >= p.n;
+        const uint32_t idesc = narrow ? idesc_half : idesc_full;
         ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1, nullptr, 12);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBlockN;
