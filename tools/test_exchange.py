@@ -34,6 +34,20 @@ def main():
         dist.broadcast(ref, 0)
         same = same and torch.equal(ref, k2)
         ok = ok and same
+    # the sharded answer must equal the answer of one GPU holding the whole gallery (rank 0 gathers the shards)
+    parts = [torch.empty(sharded.shard_bounds(n, world, r)[1] - sharded.shard_bounds(n, world, r)[0], dim,
+                         dtype=torch.bfloat16, device=dev) if rank == 0 else None for r in range(world)]
+    if rank == 0:
+        parts[0].copy_(gal)
+        for r in range(1, world):
+            dist.recv(parts[r], src=r)
+        whole = torch.cat(parts)
+        _, i_one, _, _ = ops.sim_topk(pred, whole, k)
+        single_ok = torch.equal(i_one, i2)
+        del whole
+    else:
+        dist.send(gal, dst=0)
+        single_ok = True
     # timing of the two exchanges (small shard so that the exchange is visible)
     res = {}
     for ex in ("nccl", "p2p"):
@@ -50,6 +64,7 @@ def main():
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("EXCHANGE_OK" if int(flag.item()) == 1 else "EXCHANGE_MISMATCH", res)
+        print("SINGLE_GPU_EQUAL" if single_ok else "SINGLE_GPU_MISMATCH")
     dist.destroy_process_group()
 
 
