@@ -321,8 +321,8 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
 
   CUtensorMap tq, tg;
   if (mode == ERN_MODE_BF16) {
-    if (dim % 64 != 0 || dim > 640) {
-      set_error("bf16 scoring needs dim %% 64 == 0 and dim <= 640 (got %d); zero-pad the features", dim);
+    if (dim % 64 != 0 || dim > 768) {
+      set_error("bf16 scoring needs dim %% 64 == 0 (zero-pad the features) and dim <= 768 (got %d)", dim);
       return ERN_ERR_UNSUPPORTED;
     }
     ERN_REQUIRE((reinterpret_cast<uintptr_t>(queries_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(gallery_dev) & 15) == 0 &&

@@ -196,7 +196,7 @@ ERN_API int ern_dvr_encode(const ern_dvr_weights* w, int dim, int heads, int pat
  *             growth == 1 selects the overflow-proof conservative schedule
  *   status_dev int32[4]: [0] != 0 => a candidate list overflowed (pathologically ordered gallery):
  *             results are NOT exact, call again with growth = 1.
- * MODE_BF16 requires dim % 64 == 0, dim <= 640 and 16-byte aligned rows.
+ * MODE_BF16 requires dim % 64 == 0, dim <= 768 and 16-byte aligned rows.
  * ------------------------------------------------------------------------------------------- */
 ERN_API size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode);
 ERN_API int ern_sim_topk(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev,

@@ -55,14 +55,14 @@ def test_fp32_validation_mode_matches_oracle(cuda_device, q, n, dim, k):
 
 
 @pytest.mark.parametrize("q,n,dim,k", [(48, 192, 640, 50), (100, 5000, 640, 100), (128, 2300, 512, 50),
-                                       (5, 130, 64, 10), (1, 4000, 640, 1)])
+                                       (5, 130, 64, 10), (1, 4000, 640, 1), (100, 9000, 768, 50), (64, 3000, 704, 20)])
 def test_bf16_single_cta_matches_oracle(cuda_device, q, n, dim, k):
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q <= 128 -> 1-CTA tcgen05 kernel
     assert stats["exact_frac"] > 0.99
 
 
 @pytest.mark.parametrize("q,n,dim,k", [(300, 5000, 640, 100), (129, 257, 640, 50), (2017, 3817, 640, 51),
-                                       (512, 40000, 512, 100), (1000, 20000, 128, 128)])
+                                       (512, 40000, 512, 100), (1000, 20000, 128, 128), (700, 30000, 768, 100)])
 def test_bf16_cta_pair_matches_oracle(cuda_device, q, n, dim, k):
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q > 128 -> cta_group::2 kernel
     assert stats["exact_frac"] > 0.99
