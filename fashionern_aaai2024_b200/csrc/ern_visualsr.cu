@@ -191,6 +191,56 @@ __global__ void finalize_kernel(const float* __restrict__ local, int64_t rows, i
   }
 }
 
+// prepare_kernel for the reference's shapes (P = 13, D = 128 * kIters): loops unrolled so that the 13 independent
+// float4 loads of a column block are in flight together
+template <int kP, int kIters>
+__global__ void __launch_bounds__(256)
+prepare_fixed_kernel(const float* __restrict__ local, int64_t rows, float* __restrict__ mean_f32,
+                     __nv_bfloat16* __restrict__ mean_b, __nv_bfloat16* __restrict__ local_b) {
+  constexpr int kDim = 128 * kIters;
+  const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= rows) return;
+  const float* x = local + b * kP * kDim + lane * 4;
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
+    float4 v[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) v[p] = *reinterpret_cast<const float4*>(x + p * kDim + it * 128);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w;
+      if (local_b) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[p].x, v[p].y), hi = __floats2bfloat162_rn(v[p].z, v[p].w);
+        *reinterpret_cast<uint2*>(local_b + (b * kP + p) * kDim + lane * 4 + it * 128) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+    const float inv = static_cast<float>(kP);
+    const float4 m = make_float4(s.x / inv, s.y / inv, s.z / inv, s.w / inv);
+    if (mean_f32) *reinterpret_cast<float4*>(mean_f32 + b * kDim + lane * 4 + it * 128) = m;
+    if (mean_b) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(m.x, m.y), hi = __floats2bfloat162_rn(m.z, m.w);
+      *reinterpret_cast<uint2*>(mean_b + b * kDim + lane * 4 + it * 128) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
+static void launch_prepare_sr(const float* local, int64_t rows, int patches, int dim, float* mean_f32,
+                              __nv_bfloat16* mean_b, __nv_bfloat16* local_b, cudaStream_t st) {
+  const int blocks = cdiv(rows * 32, 256);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(local) | reinterpret_cast<uintptr_t>(mean_f32) |
+                         reinterpret_cast<uintptr_t>(mean_b) | reinterpret_cast<uintptr_t>(local_b)) & 15u) == 0;
+  if (patches == 13 && dim == 640 && aligned)
+    prepare_fixed_kernel<13, 5><<<blocks, 256, 0, st>>>(local, rows, mean_f32, mean_b, local_b);
+  else if (patches == 13 && dim == 512 && aligned)
+    prepare_fixed_kernel<13, 4><<<blocks, 256, 0, st>>>(local, rows, mean_f32, mean_b, local_b);
+  else
+    prepare_kernel<<<blocks, 256, 0, st>>>(local, rows, patches, dim, mean_f32, mean_b, local_b);
+}
+
 // Specialisation for the reference's shapes (P = 13 patches, D = 128 * kIters): the first block of patch loads is
 // issued before the softmax weights are known, the accumulators stay in registers through the normalisation (one
 // write of the output row instead of write + re-read + write), and all loops are unrolled so that the independent
@@ -293,7 +343,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
     float* cvec = reinterpret_cast<float*>(ws + al(r * d * 4));
     float* partial = reinterpret_cast<float*>(ws + 2 * al(r * d * 4));
     const int n_tiles = cdiv(dim, kTile);
-    prepare_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, mean, nullptr, nullptr);
+    launch_prepare_sr(local, rows, patches, dim, mean, nullptr, nullptr, st);
     ERN_REQUIRE(cdiv(rows * patches, kTile) <= 65535, "too many rows for one fp32 VisualSR call; split the batch");
     linear_tanh_f32_kernel<false><<<dim3(n_tiles, cdiv(rows, kTile)), kF32Threads, 0, st>>>(
         mean, rows, w->w_global, dim, dim, w->b_global, w->bn_global_scale, w->bn_global_shift, w->w_common, cvec,
@@ -314,7 +364,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
   const uint8_t* pk = static_cast<const uint8_t*>(w->packed_bf16);
   const void* wl_b = pk;
   const void* wg_b = pk + al(d * d * 2);
-  prepare_kernel<<<warp_blocks, 256, 0, st>>>(local, rows, patches, dim, nullptr, mean_b, local_b);
+  launch_prepare_sr(local, rows, patches, dim, nullptr, mean_b, local_b, st);
   ERN_CUDA(cudaGetLastError());
   CUtensorMap t_local, t_mean, t_wl, t_wg;
   int rc;
