@@ -307,6 +307,18 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// ldmatrix: four / two 8x8 bf16 matrices from shared memory in the mma fragment layout (lane l supplies the address
+// of row l % 8 of matrix l / 8); .trans hands out the transposed fragments, i.e. B fragments from a row-major [k][n] tile
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -317,12 +329,15 @@ __global__ void __launch_bounds__(192)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __nv_bfloat16* __restrict__ K, int64_t ldk,
                      const __nv_bfloat16* __restrict__ V, int64_t ldv, __nv_bfloat16* __restrict__ O, int64_t ldo,
                      int Lq, int Lk, float scale) {
-  constexpr int QP = kDh + 8;          // row pitch (bf16) of Qs / Ks: 12 g + t bank pattern, conflict-free fragments
-  constexpr int VP = kAttnLmax + 8;    // row pitch of the transposed V
+  // Q, K and V head slices are staged row-major with a pitch of kDh + 8 bf16 (16-byte rows at a 4-bank skew of
+  // 12: every 8-row ldmatrix phase is bank-conflict free).  All fragments come from ldmatrix: x4 for the A (Q)
+  // and B (K) operands of Q.K^T, x4.trans for the B operand of P.V straight from row-major V -- no transposed copy
+  // (the earlier scalar transposing stores, 8 per loaded vector, were the longest phase of this kernel).
+  constexpr int QP = kDh + 8;
   extern __shared__ __align__(16) uint8_t sm_raw[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
   __nv_bfloat16* Ks = Qs + kAttnLmax * QP;
-  __nv_bfloat16* Vt = Ks + kAttnLmax * QP;   // [kDh][VP]
+  __nv_bfloat16* Vs = Ks + kAttnLmax * QP;
   const int h = blockIdx.x;
   const int64_t b = blockIdx.y;
   const int tid = threadIdx.x;
@@ -338,9 +353,7 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __n
     }
     *reinterpret_cast<uint4*>(Qs + r * QP + v * 8) = q4;
     *reinterpret_cast<uint4*>(Ks + r * QP + v * 8) = k4;
-    const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(&v4);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) Vt[(v * 8 + u) * VP + r] = vv[u];
+    *reinterpret_cast<uint4*>(Vs + r * QP + v * 8) = v4;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -349,6 +362,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __n
   if (m0 >= Lq) return;
   const int ntiles = (Lk + 7) >> 3;      // 8-column score tiles
   const int ktiles = (Lk + 15) >> 4;     // 16-deep steps of P V
+  // per-lane row / column offsets of the ldmatrix addresses
+  const int lrow8 = lane & 7, lmat = lane >> 3;     // row within an 8x8 matrix, which of the 4 matrices
 
   float sacc[12][4];
 #pragma unroll
@@ -357,17 +372,17 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __n
     for (int i = 0; i < 4; ++i) sacc[nt][i] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < kDh / 16; ++kk) {
+    // A: matrices (rows m0..+7 | m0+8..+15) x (cols kk*16..+7 | +8..+15) -> a[0..3]
     uint32_t a[4];
-    a[0] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g) * QP + kk * 16 + 2 * t);
-    a[1] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g + 8) * QP + kk * 16 + 2 * t);
-    a[2] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g) * QP + kk * 16 + 2 * t + 8);
-    a[3] = *reinterpret_cast<const uint32_t*>(Qs + (m0 + g + 8) * QP + kk * 16 + 2 * t + 8);
+    ldmatrix_x4(a, Qs + (m0 + lrow8 + (lmat & 1) * 8) * QP + kk * 16 + (lmat >> 1) * 8);
 #pragma unroll
-    for (int nt = 0; nt < 12; ++nt) {
-      if (nt < ntiles) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * QP + kk * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + g) * QP + kk * 16 + 2 * t + 8);
-        mma_bf16_16816(sacc[nt], a, b0, b1);
+    for (int np = 0; np < 6; ++np) {       // two 8-key tiles per ldmatrix.x4
+      if (2 * np < ntiles) {
+        // B: matrices (keys 16np..+7, d kk*16..+7), (same keys, d +8), (keys 16np+8..+15, d ..), (.., d +8)
+        uint32_t bb[4];
+        ldmatrix_x4(bb, Ks + (np * 16 + lrow8 + (lmat >> 1) * 8) * QP + kk * 16 + (lmat & 1) * 8);
+        mma_bf16_16816(sacc[2 * np], a, bb[0], bb[1]);
+        mma_bf16_16816(sacc[2 * np + 1], a, bb[2], bb[3]);
       }
     }
   }
@@ -417,10 +432,12 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ Q, int64_t ldq, const __n
       a[2] = pack2_bf16(sacc[2 * kt + 1][0] * inv0, sacc[2 * kt + 1][1] * inv0);
       a[3] = pack2_bf16(sacc[2 * kt + 1][2] * inv1, sacc[2 * kt + 1][3] * inv1);
 #pragma unroll
-      for (int dn = 0; dn < kDh / 8; ++dn) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(Vt + (dn * 8 + g) * VP + kt * 16 + 2 * t);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(Vt + (dn * 8 + g) * VP + kt * 16 + 2 * t + 8);
-        mma_bf16_16816(oacc[dn], a, b0, b1);
+      for (int dp = 0; dp < kDh / 16; ++dp) {   // two 8-wide output column tiles per ldmatrix.x4.trans
+        // row-major V[key][d]: matrices (keys kt*16..+7 | +8..+15) x (d 16dp..+7 | +8..+15), transposed on load
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, Vs + (kt * 16 + lrow8 + (lmat & 1) * 8) * QP + dp * 16 + (lmat >> 1) * 8);
+        mma_bf16_16816(oacc[2 * dp], a, bb[0], bb[1]);
+        mma_bf16_16816(oacc[2 * dp + 1], a, bb[2], bb[3]);
       }
     }
   }
@@ -437,7 +454,7 @@ template <int kDh>
 static int launch_attention_mma(const __nv_bfloat16* Q, int64_t ldq, const __nv_bfloat16* K, int64_t ldk,
                                 const __nv_bfloat16* V, int64_t ldv, __nv_bfloat16* O, int64_t ldo, int64_t batch,
                                 int heads, int Lq, int Lk, cudaStream_t st) {
-  constexpr size_t smem = (2 * kAttnLmax * (kDh + 8) + kDh * (kAttnLmax + 8)) * 2;
+  constexpr size_t smem = 3 * kAttnLmax * (kDh + 8) * 2;
   auto kern = attention_mma_kernel<kDh>;
   static bool configured[64] = {};
   int dev = 0;
