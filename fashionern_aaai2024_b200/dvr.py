@@ -62,7 +62,8 @@ class DVR_module(nn.Module):  # noqa: N801  (the reference's class name)
         self.combiner_local = CombinerSimple(d, d * 4, d * 8, mode=mode)
         self.combiner = CombinerSimple(d, d * 4, d * 8, mode=mode)
         self.mode = mode
-        self.max_batch = 512                       # queries per kernel chain (bounds the workspace)
+        self.max_batch = 2048                      # queries per kernel chain (bounds the workspace: ~1.5 MB per query;
+                                                   # measured 14.3 / 13.7 / 13.2 / 13.1 ms per 4096 queries at 512 / 1024 / 2048 / 4096)
         self._packed: Optional[torch.Tensor] = None
         self._versions = None
         if device is not None:
