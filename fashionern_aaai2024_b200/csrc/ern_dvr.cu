@@ -124,9 +124,13 @@ __global__ void embed_ln_kernel(const float* __restrict__ patches, const float* 
   layer_norm_row<kVec>(v, dim, lane, w, b, X + r * dim, Xb ? Xb + r * dim : nullptr);
 }
 
+// out = LayerNorm(in + res) (res nullable).  In bf16 mode the residual is added HERE rather than in the epilogue of
+// the preceding GEMM: a streaming kernel reads it at full bandwidth, whereas in the epilogue its global loads sat on
+// the critical path of every 32-column chunk.  Same rounding sequence either way ((acc + bias) then + residual).
 template <bool kVec>
-__global__ void layernorm_kernel(const float* __restrict__ in, int64_t rows, int dim, const float* __restrict__ w,
-                                 const float* __restrict__ b, float* __restrict__ out, __nv_bfloat16* __restrict__ out_b) {
+__global__ void layernorm_kernel(const float* __restrict__ in, const float* res, int64_t rows, int dim,
+                                 const float* __restrict__ w, const float* __restrict__ b, float* out,
+                                 __nv_bfloat16* __restrict__ out_b) {   // res may alias out (in-place residual stream)
   const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -135,7 +139,14 @@ __global__ void layernorm_kernel(const float* __restrict__ in, int64_t rows, int
 #pragma unroll
     for (int j = 0; j < kMaxPerLane / 4; ++j) {
       const int d = 4 * lane + 128 * j;
-      const float4 x = d < dim ? *reinterpret_cast<const float4*>(in + r * dim + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d < dim) {
+        x = *reinterpret_cast<const float4*>(in + r * dim + d);
+        if (res) {
+          const float4 y = *reinterpret_cast<const float4*>(res + r * dim + d);
+          x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        }
+      }
       v[4 * j + 0] = x.x;
       v[4 * j + 1] = x.y;
       v[4 * j + 2] = x.z;
@@ -145,7 +156,7 @@ __global__ void layernorm_kernel(const float* __restrict__ in, int64_t rows, int
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; ++i) {
       const int d = lane + 32 * i;
-      v[i] = d < dim ? in[r * dim + d] : 0.f;
+      v[i] = d < dim ? in[r * dim + d] + (res ? res[r * dim + d] : 0.f) : 0.f;
     }
   }
   layer_norm_row<kVec>(v, dim, lane, w, b, out + r * dim, out_b ? out_b + r * dim : nullptr);
@@ -157,13 +168,13 @@ static bool aligned16(std::initializer_list<const void*> ptrs) {
     if (q && (reinterpret_cast<uintptr_t>(q) & 15u)) return false;
   return true;
 }
-static void launch_layernorm(const float* in, int64_t rows, int dim, const float* w, const float* b, float* out,
-                             __nv_bfloat16* out_b, cudaStream_t st) {
+static void launch_layernorm(const float* in, const float* res, int64_t rows, int dim, const float* w, const float* b,
+                             float* out, __nv_bfloat16* out_b, cudaStream_t st) {
   const int blocks = cdiv(rows * 32, 256);
-  if (dim % 128 == 0 && aligned16({in, w, b, out, out_b}))
-    layernorm_kernel<true><<<blocks, 256, 0, st>>>(in, rows, dim, w, b, out, out_b);
+  if (dim % 128 == 0 && aligned16({in, res, w, b, out, out_b}))
+    layernorm_kernel<true><<<blocks, 256, 0, st>>>(in, res, rows, dim, w, b, out, out_b);
   else
-    layernorm_kernel<false><<<blocks, 256, 0, st>>>(in, rows, dim, w, b, out, out_b);
+    layernorm_kernel<false><<<blocks, 256, 0, st>>>(in, res, rows, dim, w, b, out, out_b);
 }
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
@@ -692,10 +703,10 @@ int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode,
       if ((rc = gemmf32::launch<gemmf32::kActNone>(ws.X, dim, M, lw.wv, dim, dim, lw.bv, nullptr, qkv + 2 * dim, 3 * dim, st))) return rc;
       if ((rc = run_attention<float>(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ctx, dim, batch, heads, L, L, dh, st))) return rc;
       if ((rc = gemmf32::launch<gemmf32::kActNone>(ctx, dim, M, lw.wo, dim, dim, lw.bo, ws.X, ws.Y, dim, st))) return rc;
-      launch_layernorm(ws.Y, M, dim, lw.ln1_w, lw.ln1_b, ws.X, nullptr, st);
+      launch_layernorm(ws.Y, nullptr, M, dim, lw.ln1_w, lw.ln1_b, ws.X, nullptr, st);
       if ((rc = gemmf32::launch<gemmf32::kActGelu>(ws.X, dim, M, lw.wi, dim, I, lw.bi, nullptr, hbuf, I, st))) return rc;
       if ((rc = gemmf32::launch<gemmf32::kActNone>(hbuf, I, M, lw.wo2, I, dim, lw.bo2, ws.X, ws.Y, dim, st))) return rc;
-      launch_layernorm(ws.Y, M, dim, lw.ln2_w, lw.ln2_b, ws.X, nullptr, st);
+      launch_layernorm(ws.Y, nullptr, M, dim, lw.ln2_w, lw.ln2_b, ws.X, nullptr, st);
     } else {
       const uint8_t* b = pk + pl.layer_stride * li;
       __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws.QKV);
@@ -712,11 +723,11 @@ int encode(const ern_dvr_weights* w, int dim, int heads, int P, int T, int mode,
         if ((rc = tc_gemm<gemmtc::kEpiBiasBf16>(Xb, M, dim, b + pl.wv, dim, lw.bv, qkv, 3 * dim, 2 * dim, nullptr, nullptr, sm_count, st))) return rc;
       }
       if ((rc = run_attention<__nv_bfloat16>(qkv, 3 * dim, qkv + dim, 3 * dim, qkv + 2 * dim, 3 * dim, ctx, dim, batch, heads, L, L, dh, st))) return rc;
-      if ((rc = tc_gemm<gemmtc::kEpiResidF32>(ctx, M, dim, b + pl.wo, dim, lw.bo, nullptr, dim, 0, ws.Y, ws.X, sm_count, st))) return rc;
-      launch_layernorm(ws.Y, M, dim, lw.ln1_w, lw.ln1_b, ws.X, Xb, st);
+      if ((rc = tc_gemm<gemmtc::kEpiResidF32>(ctx, M, dim, b + pl.wo, dim, lw.bo, nullptr, dim, 0, ws.Y, nullptr, sm_count, st))) return rc;
+      launch_layernorm(ws.Y, ws.X, M, dim, lw.ln1_w, lw.ln1_b, ws.X, Xb, st);   // + residual, in place over it
       if ((rc = tc_gemm<gemmtc::kEpiGeluBf16>(Xb, M, dim, b + pl.wi, I, lw.bi, hbuf, I, 0, nullptr, nullptr, sm_count, st))) return rc;
-      if ((rc = tc_gemm<gemmtc::kEpiResidF32>(hbuf, M, I, b + pl.wo2, dim, lw.bo2, nullptr, dim, 0, ws.Y, ws.X, sm_count, st))) return rc;
-      launch_layernorm(ws.Y, M, dim, lw.ln2_w, lw.ln2_b, ws.X, Xb, st);
+      if ((rc = tc_gemm<gemmtc::kEpiResidF32>(hbuf, M, I, b + pl.wo2, dim, lw.bo2, nullptr, dim, 0, ws.Y, nullptr, sm_count, st))) return rc;
+      launch_layernorm(ws.Y, ws.X, M, dim, lw.ln2_w, lw.ln2_b, ws.X, Xb, st);
     }
     ERN_CUDA(cudaGetLastError());
   }
