@@ -11,11 +11,11 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MAX_K, MODE_BF16, MODE_FP32, RANK_REFERENCE,
+from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, RANK_REFERENCE,
                    RANK_SIMILARITY, SORT_CAP, ErnError)
 
 __all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "gather_scores",
-           "cirr_subset_from_scores", "launch_counter"]
+           "cirr_subset_from_scores", "bbc_loss_forward", "bbc_loss_backward", "launch_counter"]
 
 
 class _LaunchCounter:

@@ -18,7 +18,7 @@ Reference lines followed by each function are cited in its docstring (paths rela
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -22,7 +22,7 @@ import re
 import sys
 import types
 import warnings
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List
 
 import torch
 

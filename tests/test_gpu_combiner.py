@@ -1,5 +1,4 @@
 """GPU: the fusion head (ern_combiner_forward) against the reference goldens and the CPU oracle."""
-import numpy as np
 import pytest
 import torch
 

@@ -5,7 +5,7 @@ import torch
 
 from oracle import ern_oracle as orc
 from fashionern_aaai2024_b200 import ops, synthetic as syn
-from fashionern_aaai2024_b200._lib import (MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARITY, ErnError)
+from fashionern_aaai2024_b200._lib import MODE_BF16, MODE_FP32, RANK_REFERENCE, RANK_SIMILARITY
 
 pytestmark = pytest.mark.gpu
 

@@ -1,5 +1,4 @@
 """CPU (+ one GPU case): packed feature store round trip, sharded loader coverage, id gathers."""
-import numpy as np
 import pytest
 import torch
 
