@@ -80,11 +80,10 @@ static SimWorkspace carve_sim(void* base, int64_t nq) {
 
 // test hook: ERN_FORCE_SINGLE_CTA=1 makes the tensor-core path use the 1-CTA kernel even for large batches
 static int force_single() {
-  static int v = -1;
-  if (v < 0) {
+  static const int v = [] {
     const char* e = getenv("ERN_FORCE_SINGLE_CTA");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
   return v;
 }
 

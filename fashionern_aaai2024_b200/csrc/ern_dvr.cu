@@ -467,12 +467,12 @@ static int launch_attention_mma(const __nv_bfloat16* Q, int64_t ldq, const __nv_
                                 int heads, int Lq, int Lk, cudaStream_t st) {
   constexpr size_t smem = 3 * kAttnLmax * (kDh + 8) * 2;
   auto kern = attention_mma_kernel<kDh>;
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64];   // zero-initialised; idempotent per-device attribute set
   int dev = 0;
   ERN_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(kDh));
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {

@@ -454,12 +454,12 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const Params& p,
   auto kern = gemm_tc_kernel<kBlockN, kEpi, kPair>;
   constexpr int smem = smem_bytes_v<kBlockN, kPair>();
   // the opt-in shared-memory size is a per-device function attribute
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64];   // zero-initialised; idempotent per-device attribute set
   int dev = 0;
   ERN_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   constexpr int kCta = kPair ? 2 : 1;
   const int64_t tiles = ((p.m + kBlockM * kCta - 1) / (kBlockM * kCta)) * n_tiles_of<kBlockN>(p.n);

@@ -331,12 +331,12 @@ template <bool kPair, int kRankBy>
 static int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const Params& p, int grid, cudaStream_t st) {
   auto kern = sim_topk_tc_kernel<kPair, kRankBy>;
   // the opt-in shared-memory size is a per-device function attribute
-  static bool configured[64] = {};
+  static std::atomic<bool> configured[64];   // zero-initialised; idempotent per-device attribute set
   int dev = 0;
   ERN_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
     ERN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
+    if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -380,11 +380,9 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, in
   const bool pair = !force_single && sink.nq > kBlockQ;
   const int tile_g = pair ? 256 : 128;
   Params p;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("ERN_DEBUG_FLAGS"); dbg = e ? atoi(e) : 0; }
+  static const int dbg = [] { const char* e = getenv("ERN_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
-  static int pf = -1;
-  if (pf < 0) { const char* e = getenv("ERN_PREFETCH_TILES"); pf = e ? atoi(e) : 0; }
+  static const int pf = [] { const char* e = getenv("ERN_PREFETCH_TILES"); return e ? atoi(e) : 0; }();
   p.gallery_base = (ldg == dim) ? static_cast<const uint8_t*>(gallery) : nullptr;
   p.gallery_rows = gallery_rows;
   p.row_bytes = dim * 2;
