@@ -10,7 +10,8 @@ synthetic gallery, 4096-query batches, gallery row-sharded over N B200s of one b
 One STEP = one batch of 4096 composed queries through the whole hot path:
     fusion head (CombinerSimple: image+text CLIP features -> unit-norm query, tcgen05 GEMMs)
  -> bf16 cosine scoring of the batch against this rank's gallery shard with streaming top-100 (tcgen05)
- -> [N > 1] NCCL all-gather of the (score,id) candidate keys + device k-way merge
+ -> [N > 1] exchange of the (score,id) candidate keys (fused peer-memory stores over NVLink, or NCCL all-gather
+    with --exchange nccl) + device k-way merge
  -> Recall@{1,10,50,100} hit counts from id membership on device.
 `value`  : queries/s of the whole job with every input already resident in HBM (CUDA events, max over ranks).
 `e2e`    : same metric through the public API with HOST inputs: per step the query batch's image/text features
