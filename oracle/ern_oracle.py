@@ -324,7 +324,8 @@ def compare_topk(cand_ids: np.ndarray, cand_scores: Optional[np.ndarray], pred: 
     worst = float(gap.max()) if gap.numel() else 0.0
     assert worst <= tol, f"rank-wise oracle similarity differs by {worst} > tol {tol}"
     if exclude_index is not None:
-        assert not bool((cand == exclude_index.long()[:, None]).any()), "excluded id was returned"
+        # padding (-1) never counts: a query without an exclusion carries exclude_index == -1
+        assert not bool(((cand == exclude_index.long()[:, None]) & (cand >= 0)).any()), "excluded id was returned"
     out = {"exact_frac": float((cand == ids_o)[valid].float().mean()) if valid.any() else 1.0,
            "max_rank_gap": worst}
     if cand_scores is not None:

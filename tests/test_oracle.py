@@ -132,3 +132,16 @@ def test_loss_restatement_matches_reference(dim):
     d[3, 5] = eps
     num = (orc.bbc_loss(pred + d, tar)[0] - orc.bbc_loss(pred - d, tar)[0]) / (2 * eps)
     assert abs(num - dp[3, 5]) < 1e-6 + 1e-4 * abs(dp[3, 5])
+
+
+def test_compare_topk_padding_is_not_an_excluded_id():
+    # gallery smaller than k: rows are padded with -1, and a query WITHOUT an exclusion carries exclude_index == -1
+    p, g = syn.features(1, 3, 16, unit=True), syn.features(2, 2, 16, unit=True)
+    excl = torch.tensor([-1, 0, 1])
+    ids, _ = orc.rank_topk(p, g, 5, exclude_index=excl)
+    assert (ids[0] >= 0).sum() == 2 and (ids[1] >= 0).sum() == 1
+    orc.compare_topk(ids.numpy(), None, p, g, 5, tol=1e-6, exclude_index=excl)
+    bad = ids.clone()
+    bad[1, 1] = 0                                   # returns the excluded row 0 for query 1
+    with pytest.raises(AssertionError):
+        orc.compare_topk(bad.numpy(), None, p, g, 5, tol=1e-6, exclude_index=excl)
