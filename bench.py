@@ -328,13 +328,15 @@ def main():
     achieved = flop_rank / (sim_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_sustained"],
-                # dram__bytes_read+write of ONE profiled launch of this kernel (ncu --set full, rows [1M, 8.4M) of a
-                # 10M-row gallery, profiles/r01_sim_topk_tc_10m_ncu_full_raw.csv) next to its algorithmic bytes
-                "traffic": 11.334e9, "traffic_algorithmic": 9.395e9,
+                # dram__bytes_read+write of ONE profiled launch of this kernel inside THIS command (ncu --set full, the
+                # launch over gallery rows [25.2M, 33.6M) of the 100M-row bench,
+                # profiles/r01_sim_topk_tc_100m_capped_ncu_full_raw.csv) next to its algorithmic bytes
+                "traffic": 12.844e9, "traffic_algorithmic": 10.737e9,
                 "achieved_basis": "2*Q*rows*D FLOP of this rank's shard / CUDA-event time of the scoring call of one step "
                                   "(all launches of the kernel plus the interleaved selection launches)",
-                "traffic_basis": "one launch: rows [1048576, 8388608) x 4096 queries, ncu --set full "
-                                 "(profiles/r01_sim_topk_tc_10m_ncu_full_raw.csv); 1.20x the gallery bytes of that launch",
+                "traffic_basis": "one launch: 8388608 gallery rows x 4096 queries of the 100M-row bench, ncu --set full "
+                                 "(profiles/r01_sim_topk_tc_100m_capped_ncu_full_raw.csv); 1.20x the gallery bytes of that "
+                                 "launch (3.0x before launches were capped at ERN_PHASE_MAX_ROWS rows)",
                 "kernel": "ern::simtc::sim_topk_tc_kernel (all launches of one step incl. the interleaved "
                           "select_topk_kernel launches, CUDA events on the launching stream)",
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",

@@ -363,7 +363,8 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
 
   // Threshold schedule.  Launch 0 keeps every score of the first ERN_DENSE_ROWS rows; each later launch
   // covers rows [b, growth*b) with the threshold fixed at the exact k-th best of rows [0, b): the expected
-  // number of survivors per query and launch is (growth-1)*k, independent of the gallery size.
+  // number of survivors per query and launch is (growth-1)*k, independent of the gallery size (fewer once the
+  // ERN_PHASE_MAX_ROWS cap takes over: k * rows-in-launch / b).
   // growth == 1: fixed steps of ERN_SORT_CAP - k rows written by a single chunk -- cannot overflow.
   int64_t begin = 0;
   bool first = true;
@@ -375,6 +376,7 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
       end = begin + (ERN_SORT_CAP - k);
     } else {
       end = begin * growth;
+      if (end - begin > ERN_PHASE_MAX_ROWS) end = begin + ERN_PHASE_MAX_ROWS;   // keep the chunks L2-friendly
     }
     if (end > n_rows) end = n_rows;
     sink.dense = first ? 1 : 0;

@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, RANK_REFERENCE,
+from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, PHASE_MAX_ROWS, RANK_REFERENCE,
                    RANK_SIMILARITY, SORT_CAP, ErnError)
 
 __all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "gather_scores",
@@ -65,7 +65,7 @@ def _phase_count(n_rows: int, k: int, growth: int) -> int:
     """Number of scoring launches ern_sim_topk issues (mirrors the schedule in csrc/ern_capi.cu)."""
     n, begin = 1, min(n_rows, DENSE_ROWS)
     while begin < n_rows:
-        begin = begin + (SORT_CAP - k) if growth == 1 else begin * growth
+        begin = begin + (SORT_CAP - k) if growth == 1 else min(begin * growth, begin + PHASE_MAX_ROWS)
         n += 1
     return n
 

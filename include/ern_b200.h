@@ -63,6 +63,10 @@ extern "C" {
 #define ERN_MAX_CHUNKS 256
 /* gallery rows scored densely (every score kept) before thresholds exist */
 #define ERN_DENSE_ROWS 256
+/* most gallery rows one scoring launch covers: the query tiles of a batch sweep each gallery chunk together and share
+ * it through L2; a chunk longer than ~500 tiles lets them drift apart (measured: 3.0x the gallery bytes from DRAM on a
+ * 58.7M-row launch against 1.2x on a 7.3M-row one), so long ranges are cut into launches of at most this many rows */
+#define ERN_PHASE_MAX_ROWS 8388608
 
 ERN_API int ern_version(void);
 ERN_API const char* ern_last_error(void);

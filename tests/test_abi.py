@@ -36,6 +36,7 @@ def test_version_and_constants():
     assert int(re.search(r"#define ERN_LIST_CAP (\d+)", src).group(1)) == _lib.LIST_CAP
     assert int(re.search(r"#define ERN_SORT_CAP (\d+)", src).group(1)) == _lib.SORT_CAP
     assert int(re.search(r"#define ERN_DENSE_ROWS (\d+)", src).group(1)) == _lib.DENSE_ROWS
+    assert int(re.search(r"#define ERN_PHASE_MAX_ROWS (\d+)", src).group(1)) == _lib.PHASE_MAX_ROWS
     assert lib.ern_sim_topk_workspace_bytes(4096, 640, 0) >= 4096 * _lib.LIST_CAP * 8
     assert lib.ern_combiner_packed_bytes(640) >= (8 * 640 * 640 + 64 * 640 * 640) * 2
 

@@ -32,7 +32,9 @@ def test_phase_schedule():
     # dense launch over the first 256 rows, then x8 gallery ranges (csrc/ern_capi.cu)
     assert _phase_count(100, 50, 8) == 1 and _phase_count(256, 50, 8) == 1
     assert _phase_count(257, 50, 8) == 2 and _phase_count(2048, 50, 8) == 2 and _phase_count(2049, 50, 8) == 3
-    assert _phase_count(1_000_000, 100, 8) == 5 and _phase_count(100_000_000, 100, 8) == 8
+    # 256, 2k, 16k, 131k, 1M, 8.4M, then steps of ERN_PHASE_MAX_ROWS (8.4M): 16.8M, 25.2M, ... 100M
+    assert _phase_count(1_000_000, 100, 8) == 5 and _phase_count(10_000_000, 100, 8) == 7
+    assert _phase_count(100_000_000, 100, 8) == 6 + 11
     assert _phase_count(10_000, 100, 1) == 1 + -(-(10_000 - 256) // (2048 - 100))
 
 
