@@ -19,8 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libern_b200.so")
 MODE_BF16, MODE_FP32 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 RANK_SIMILARITY, RANK_REFERENCE = 0, 1
-MAX_K, LIST_CAP, SORT_CAP, MAX_CHUNKS, DENSE_ROWS = 128, 4096, 2048, 256, 256
-PHASE_MAX_ROWS = 1 << 23
+MAX_K, SEG_CAP, SORT_CAP, QUERY_BATCH, DENSE_ROWS = 128, 256, 2048, 4096, 256
 
 # every symbol include/ern_b200.h declares; tests check the .so exports exactly these
 SYMBOLS = (

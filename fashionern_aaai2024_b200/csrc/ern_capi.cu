@@ -49,34 +49,34 @@ static int current_device(DeviceInfo* out) {
 static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct SimWorkspace {
-  uint64_t* lists;
+  uint64_t* prefix;
+  uint64_t* segs;
   int32_t* prev_counts;
   int32_t* seg_counts;
-  float* thr;
+  uint32_t* thr_ord;
   size_t bytes;
 };
-// slots per query: small batches get longer lists so that the gallery can be cut into more (smaller) chunks
-static int list_cap(int64_t nq) { return nq <= 1024 ? 4 * ERN_LIST_CAP : ERN_LIST_CAP; }
-// every segment keeps >= 62 slots: >= 5x the expected survivors per chunk at growth 8, k <= 128
-static int chunk_limit(int cap, int keep) {
-  const int c = (cap - keep) / 62;
-  return c < 1 ? 1 : (c > ERN_MAX_CHUNKS ? ERN_MAX_CHUNKS : c);
-}
-static SimWorkspace carve_sim(void* base, int64_t nq) {
+// One query batch (<= ERN_QUERY_BATCH queries) at a time goes through the launch schedule; the workspace holds the
+// candidate storage of one batch: per query a 256-slot prefix and n_seg segments of seg_cap slots (CandidateSink).
+static SimWorkspace carve_sim(void* base, int64_t batch, int n_seg, int seg_cap) {
   SimWorkspace w;
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
-  w.lists = reinterpret_cast<uint64_t*>(p + off);
-  off += align256(static_cast<size_t>(nq) * list_cap(nq) * 8);
+  w.prefix = reinterpret_cast<uint64_t*>(p + off);
+  off += align256(static_cast<size_t>(batch) * ERN_DENSE_ROWS * 8);
+  w.segs = reinterpret_cast<uint64_t*>(p + off);
+  off += align256(static_cast<size_t>(batch) * n_seg * seg_cap * 8);
   w.prev_counts = reinterpret_cast<int32_t*>(p + off);
-  off += align256(static_cast<size_t>(nq) * 4);
+  off += align256(static_cast<size_t>(batch) * 4);
   w.seg_counts = reinterpret_cast<int32_t*>(p + off);
-  off += align256(static_cast<size_t>(nq) * ERN_MAX_CHUNKS * 4);
-  w.thr = reinterpret_cast<float*>(p + off);
-  off += align256(static_cast<size_t>(nq) * 4);
+  off += align256(static_cast<size_t>(batch) * n_seg * 4);
+  w.thr_ord = reinterpret_cast<uint32_t*>(p + off);
+  off += align256(static_cast<size_t>(batch) * 4);
   w.bytes = off;
   return w;
 }
+// slots per segment: room for k survivors plus at least 64 appends between two in-kernel compactions
+static int seg_cap_for(int k) { return k <= 64 ? 128 : ERN_SEG_CAP; }
 
 // test hook: ERN_FORCE_SINGLE_CTA=1 makes the tensor-core path use the 1-CTA kernel even for large batches
 static int force_single() {
@@ -284,11 +284,29 @@ int ern_visualsr_forward(const ern_visualsr_weights* w, int dim, int patches, in
 }
 
 // ---------------------------------------------------------------------------------------------------------
+static int sm_count_or_default() {
+  int dev = -1, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    return sms;
+  (void)cudaGetLastError();
+  return 148;   // B200
+}
+
 size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode) {
   (void)dim;
   (void)mode;
   if (nq < 0) return 0;
-  return carve_sim(nullptr, nq).bytes + 256;
+  // two batch shapes occur: full batches and the remainder (which may run on the 1-CTA kernel with more units)
+  const int sms = sm_count_or_default();
+  const int64_t full = nq < ERN_QUERY_BATCH ? nq : ERN_QUERY_BATCH;
+  const int64_t rem = nq % ERN_QUERY_BATCH;
+  size_t bytes = carve_sim(nullptr, full, simtc::units_for(full, force_single(), sms), ERN_SEG_CAP).bytes;
+  if (rem > 0) {
+    const size_t b2 = carve_sim(nullptr, rem, simtc::units_for(rem, force_single(), sms), ERN_SEG_CAP).bytes;
+    if (b2 > bytes) bytes = b2;
+  }
+  return bytes + 256;
 }
 
 static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const void* gallery_dev, int64_t n_rows,
@@ -316,9 +334,7 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
     set_error("workspace too small: %zu < %zu", workspace_bytes, ern_sim_topk_workspace_bytes(nq, dim, mode));
     return ERN_ERR_WORKSPACE;
   }
-  SimWorkspace ws = carve_sim(workspace_dev, nq);
-
-  CUtensorMap tq, tg;
+  const int esize = mode == ERN_MODE_BF16 ? 2 : 4;
   if (mode == ERN_MODE_BF16) {
     if (dim % 64 != 0 || dim > 768) {
       set_error("bf16 scoring needs dim %% 64 == 0 (zero-pad the features) and dim <= 768 (got %d)", dim);
@@ -327,90 +343,103 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
     ERN_REQUIRE((reinterpret_cast<uintptr_t>(queries_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(gallery_dev) & 15) == 0 &&
                     (ldq * 2) % 16 == 0 && (ldg * 2) % 16 == 0,
                 "bf16 feature rows must be 16-byte aligned");
-    rc = simtc::make_tmap_bf16_rows(&tq, queries_dev, nq, dim, ldq);
-    if (rc) return rc;
-    if (n_rows > 0) {
-      rc = simtc::make_tmap_bf16_rows(&tg, gallery_dev, n_rows, dim, ldg);
-      if (rc) return rc;
-    }
   }
+  CUtensorMap tq, tg;
+  if (mode == ERN_MODE_BF16 && n_rows > 0) {
+    rc = simtc::make_tmap_bf16_rows(&tg, gallery_dev, n_rows, dim, ldg);
+    if (rc) return rc;
+  }
+  const int seg_cap = seg_cap_for(k);
 
-  rc = launch_init_state(ws.prev_counts, ws.seg_counts, ws.thr, nq, status_dev, st);
-  if (rc) return rc;
-
-  CandidateSink sink;
-  memset(&sink, 0, sizeof(sink));
-  sink.lists = ws.lists;
-  sink.seg_counts = ws.seg_counts;
-  sink.thresholds = ws.thr;
-  sink.exclude = exclude_id_dev;
-  sink.status = status_dev;
-  sink.cap = list_cap(nq);
-  sink.keep = k;
-  sink.id_offset = id_offset;
-  sink.nq = nq;
-
-  SelectParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.lists = ws.lists;
-  sp.cap = list_cap(nq);
-  sp.keep = k;
-  sp.prev_counts = ws.prev_counts;
-  sp.seg_counts = ws.seg_counts;
-  sp.k = k;
-  sp.thresholds = ws.thr;
-  sp.status = status_dev;
-
-  // Threshold schedule.  Launch 0 keeps every score of the first ERN_DENSE_ROWS rows; each later launch
-  // covers rows [b, growth*b) with the threshold fixed at the exact k-th best of rows [0, b): the expected
-  // number of survivors per query and launch is (growth-1)*k, independent of the gallery size (fewer once the
-  // ERN_PHASE_MAX_ROWS cap takes over: k * rows-in-launch / b).
-  // growth == 1: fixed steps of ERN_SORT_CAP - k rows written by a single chunk -- cannot overflow.
-  int64_t begin = 0;
-  bool first = true;
-  do {
-    int64_t end;
-    if (first) {
-      end = ERN_DENSE_ROWS;
-    } else if (growth == 1) {
-      end = begin + (ERN_SORT_CAP - k);
-    } else {
-      end = begin * growth;
-      if (end - begin > ERN_PHASE_MAX_ROWS) end = begin + ERN_PHASE_MAX_ROWS;   // keep the chunks L2-friendly
-    }
-    if (end > n_rows) end = n_rows;
-    sink.dense = first ? 1 : 0;
-    sink.row_begin = begin;
-    sink.row_end = end;
-    sink.n_chunks = (growth == 1) ? 1 : chunk_limit(sink.cap, sink.keep);   // upper bound; the launcher picks the split
-    sink.seg_size = (sink.cap - sink.keep) / sink.n_chunks;
-    if (end > begin) {
-      if (mode == ERN_MODE_FP32) {
-        sink.n_chunks = 1;
-        sink.seg_size = sink.cap - sink.keep;
-        rc = simf32::launch(static_cast<const float*>(queries_dev), ldq, static_cast<const float*>(gallery_dev), ldg,
-                            dim, sink, rank_by, st);
-      } else {
-        rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, gallery_dev, n_rows, ldg, st);
-      }
+  // ---- query batches: each runs the whole launch schedule over the shard ------------------------------------------
+  for (int64_t q0 = 0; q0 < nq; q0 += ERN_QUERY_BATCH) {
+    const int64_t bq = nq - q0 < ERN_QUERY_BATCH ? nq - q0 : ERN_QUERY_BATCH;
+    const int n_seg = simtc::units_for(bq, force_single(), di.sm_count);
+    SimWorkspace ws = carve_sim(workspace_dev, bq, n_seg, seg_cap);
+    const uint8_t* qbase = static_cast<const uint8_t*>(queries_dev) + static_cast<size_t>(q0) * ldq * esize;
+    if (mode == ERN_MODE_BF16) {
+      rc = simtc::make_tmap_bf16_rows(&tq, qbase, bq, dim, ldq);
       if (rc) return rc;
     }
-    const bool last = end >= n_rows;
-    sp.dense_count = first ? static_cast<int>(end - begin) : 0;
-    sp.n_chunks = first ? 0 : sink.n_chunks;
-    sp.seg_size = sink.seg_size;
-    sp.out_scores = last ? out_scores_dev : nullptr;
-    sp.out_ids = last ? out_ids_dev : nullptr;
-    sp.out_keys = last ? out_keys_dev : nullptr;
-    sp.peer_keys = last ? peer_keys_dev : nullptr;
+    rc = launch_init_state(ws.prev_counts, ws.seg_counts, ws.thr_ord, bq, n_seg, q0 == 0 ? status_dev : nullptr, st);
+    if (rc) return rc;
+
+    CandidateSink sink;
+    memset(&sink, 0, sizeof(sink));
+    sink.prefix = ws.prefix;
+    sink.segs = ws.segs;
+    sink.seg_counts = ws.seg_counts;
+    sink.thr_ord = ws.thr_ord;
+    sink.exclude = exclude_id_dev ? exclude_id_dev + q0 : nullptr;
+    sink.status = status_dev;
+    sink.n_seg = n_seg;
+    sink.seg_cap = seg_cap;
+    sink.k = k;
+    sink.id_offset = id_offset;
+    sink.nq = bq;
+
+    SelectParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.prefix = ws.prefix;
+    sp.prev_counts = ws.prev_counts;
+    sp.segs = ws.segs;
+    sp.seg_counts = ws.seg_counts;
+    sp.n_seg = n_seg;
+    sp.seg_cap = seg_cap;
+    sp.single_segment = mode == ERN_MODE_FP32 ? 1 : 0;
+    sp.k = k;
+    sp.thr_ord = ws.thr_ord;
+    sp.status = status_dev;
     sp.world = world;
     sp.rank = rank;
     sp.nq_total = nq;
-    rc = launch_select(sp, nq, st);
-    if (rc) return rc;
-    begin = end;
-    first = false;
-  } while (begin < n_rows);
+    sp.q_first = q0;
+
+    // Launch schedule.  Launch 0 keeps every score of the first ERN_DENSE_ROWS rows; each later launch covers rows
+    // [b, growth*b) starting from the exact k-th best of rows [0, b) as the threshold, so on an unordered gallery
+    // about (growth-1)*k candidates per query reach the selection kernel after every launch, independent of the
+    // gallery size.  The schedule is a cost heuristic only: the tensor-core kernel bounds its segments itself
+    // (in-kernel compaction), so every launch is exact whatever the order of the rows.  The fp32 validation kernel
+    // has no compaction: its launches cover at most as many rows as a query's candidate storage has slots.
+    // growth == 1: fixed steps of ERN_SORT_CAP - k rows (test hook: many small launches).
+    const int64_t f32_rows_max = static_cast<int64_t>(n_seg) * seg_cap;
+    int64_t begin = 0;
+    bool first = true;
+    do {
+      int64_t end;
+      if (first) {
+        end = ERN_DENSE_ROWS;
+      } else if (growth == 1) {
+        end = begin + (ERN_SORT_CAP - k);
+      } else {
+        end = begin * growth;
+      }
+      if (!first && mode == ERN_MODE_FP32 && end - begin > f32_rows_max) end = begin + f32_rows_max;
+      if (end > n_rows) end = n_rows;
+      sink.dense = first ? 1 : 0;
+      sink.row_begin = begin;
+      sink.row_end = end;
+      if (end > begin) {
+        if (mode == ERN_MODE_FP32) {
+          rc = simf32::launch(reinterpret_cast<const float*>(qbase), ldq, static_cast<const float*>(gallery_dev), ldg,
+                              dim, sink, rank_by, st);
+        } else {
+          rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, gallery_dev, n_rows, ldg, st);
+        }
+        if (rc) return rc;
+      }
+      const bool last = end >= n_rows;
+      sp.dense_count = first ? static_cast<int>(end - begin) : 0;
+      sp.out_scores = (last && out_scores_dev) ? out_scores_dev + q0 * k : nullptr;
+      sp.out_ids = (last && out_ids_dev) ? out_ids_dev + q0 * k : nullptr;
+      sp.out_keys = (last && out_keys_dev) ? out_keys_dev + q0 * k : nullptr;
+      sp.peer_keys = last ? peer_keys_dev : nullptr;
+      rc = launch_select(sp, bq, st);
+      if (rc) return rc;
+      begin = end;
+      first = false;
+    } while (begin < n_rows);
+  }
   return ERN_OK;
 }
 
@@ -453,6 +482,7 @@ int ern_topk_merge(const uint64_t* keys_dev, int64_t nq, int n_lists, int k_in, 
   sp.out_scores = out_scores_dev;
   sp.out_ids = out_ids_dev;
   sp.out_keys = out_keys_dev;
+  sp.nq_total = nq;
   return launch_select(sp, nq, static_cast<cudaStream_t>(stream));
 }
 

@@ -70,26 +70,34 @@ __device__ __forceinline__ float rank_value(float s) {
 }
 
 // ---- candidate sink: where the scoring kernels put (value, id) pairs that pass the threshold --------
-// One list of `cap` 64-bit slots per query.  Slots [0, keep) hold the survivors of earlier launches.  The rest
-// is cut into `n_chunks` segments of `seg_size` slots; a segment has exactly one writer (the work item that
-// scores gallery chunk c for this query), which appends with a private register counter -- no atomics on the
-// hot path -- and publishes its count in seg_counts[q, c] when it finishes.  The fp32 validation kernel, whose
-// blocks are not aligned with chunks, uses a single segment with an atomic cursor in seg_counts[q, 0].
+// Per query:
+//   prefix  [ERN_DENSE_ROWS] keys : slots [0, prev_count) hold the exact top-k of everything scored so far (written by
+//           the selection kernel); the first ("dense") launch stores every score of the first rows here instead.
+//   segs    [n_seg][seg_cap] keys : segment u has exactly ONE writer for a whole launch -- the persistent scoring unit
+//           (CTA pair / CTA) number u -- which appends with a private register cursor (no atomics) and publishes its
+//           count in seg_counts[q, u] when it leaves the query tile.  A segment never overflows: when fewer than 32
+//           free slots remain, the owning warp selects the segment's k best keys in place (warp_compact_segment), which
+//           also yields a tighter lower bound on the query's final k-th best value; the bound is shared with every
+//           other unit through thr_ord[q] (atomicMax on the order-preserving bits).  So a launch may cover any number
+//           of gallery rows in any order and stays exact -- gallery order only changes how often segments compact.
+//   thr_ord [1] : order-preserving bits of the current lower bound (f32_to_ordered(-inf) at start).
+// The fp32 validation kernel, whose blocks are not persistent, treats the n_seg * seg_cap slots of a query as one
+// segment with an atomic cursor in seg_counts[q, 0]; its launches are sized so that it cannot overflow.
 struct CandidateSink {
-  uint64_t* lists;          // [nq, cap]
-  int32_t* seg_counts;      // [nq, ERN_MAX_CHUNKS]
-  const float* thresholds;  // [nq] current lower bound on the k-th best ranking value (-inf at start)
+  uint64_t* prefix;         // [nq, ERN_DENSE_ROWS]
+  uint64_t* segs;           // [nq, n_seg, seg_cap]
+  int32_t* seg_counts;      // [nq, n_seg]
+  uint32_t* thr_ord;        // [nq]
   const int32_t* exclude;   // [nq] global id to drop, or nullptr
   int32_t* status;          // [4]
-  int cap;
-  int keep;
-  int n_chunks;
-  int seg_size;
-  int dense;                // 1: every row of [row_begin,row_end) is stored at slot (row - row_begin)
+  int n_seg;
+  int seg_cap;
+  int k;
+  int dense;                // 1: every row of [row_begin,row_end) is stored at prefix slot (row - row_begin)
   int64_t row_begin;        // shard-local gallery rows covered by this launch
   int64_t row_end;
   int64_t id_offset;        // global id of shard row 0
-  int64_t nq;
+  int64_t nq;               // queries of this batch (the pointers above are already offset to its first query)
 };
 
 // dense launches: slot = row - row_begin, NaN scores and the excluded id become empty slots
@@ -97,16 +105,17 @@ __device__ __forceinline__ void sink_put_dense(const CandidateSink& s, int64_t q
                                                int32_t excl) {
   const uint32_t gid = static_cast<uint32_t>(row + s.id_offset);
   const bool drop = (static_cast<int32_t>(gid) == excl) || !(value == value);
-  s.lists[q * s.cap + (row - s.row_begin)] = drop ? 0ull : make_key(value, gid);
+  s.prefix[q * ERN_DENSE_ROWS + (row - s.row_begin)] = drop ? 0ull : make_key(value, gid);
 }
 // single-segment atomic append (fp32 validation kernel only)
 __device__ __forceinline__ void sink_put_atomic(const CandidateSink& s, int64_t q, int64_t row, float value,
                                                 int32_t excl) {
   const uint32_t gid = static_cast<uint32_t>(row + s.id_offset);
   if (static_cast<int32_t>(gid) == excl) return;
-  const int pos = atomicAdd(&s.seg_counts[q * ERN_MAX_CHUNKS], 1);
-  if (pos < s.seg_size) s.lists[q * s.cap + s.keep + pos] = make_key(value, gid);
+  const int pos = atomicAdd(&s.seg_counts[q * s.n_seg], 1);
+  if (pos < s.n_seg * s.seg_cap) s.segs[q * static_cast<int64_t>(s.n_seg) * s.seg_cap + pos] = make_key(value, gid);
 }
+
 
 inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 

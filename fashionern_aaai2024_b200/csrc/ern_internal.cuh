@@ -7,8 +7,8 @@ namespace ern {
 
 struct SelectParams;
 int launch_select(const SelectParams& p, int64_t nq, cudaStream_t st);
-int launch_init_state(int32_t* prev_counts, int32_t* seg_counts, float* thr, int64_t nq, int32_t* status,
-                      cudaStream_t st);
+int launch_init_state(int32_t* prev_counts, int32_t* seg_counts, uint32_t* thr_ord, int64_t nq, int n_seg,
+                      int32_t* status, cudaStream_t st);
 int launch_recall(const int32_t* top_ids, int64_t nq, int k, const int32_t* class_of, int64_t n_gallery,
                   const int32_t* target_class, const int32_t* ks, int nk, int32_t* counts, int32_t* rank_out,
                   cudaStream_t st);
@@ -31,7 +31,8 @@ int launch(const float* Q, int64_t ldq, const float* G, int64_t ldg, int dim, co
 }
 namespace simtc {
 int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int dim, int64_t ld_elems);
-int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, int dim, int rank_by,
+int units_for(int64_t nq, int force_single, int sm_count);
+int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
            int force_single, int sm_count, const void* gallery, int64_t gallery_rows, int64_t ldg, cudaStream_t st);
 }
 namespace combiner {

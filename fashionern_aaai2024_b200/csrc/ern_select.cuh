@@ -9,27 +9,29 @@ struct SelectParams {
   int64_t query_stride;
   int n_lists;
   int k_in;
-  // ---- source B (a query's own candidate list, see CandidateSink)
-  uint64_t* lists;           // [nq, cap]; the compacted top-k is written back to slots [0,k)
-  int cap;
-  int keep;                  // survivors of earlier launches live in slots [0, prev_counts[q])
+  // ---- source B (a query's own candidates, see CandidateSink): prefix slots [0, prev_counts[q]) (or [0, dense_count)
+  //      after the dense launch) + the published part of every segment.  The top-k goes back to prefix [0,k).
+  uint64_t* prefix;          // [nq, ERN_DENSE_ROWS]
   int32_t* prev_counts;      // [nq]  in: survivors, out: min(n, k)
-  int32_t* seg_counts;       // [nq, ERN_MAX_CHUNKS]; reset to 0 after reading
-  int n_chunks;
-  int seg_size;
-  int dense_count;           // > 0: slots [0, dense_count) are all candidates (first launch), segments unused
+  const uint64_t* segs;      // [nq, n_seg, seg_cap]
+  int32_t* seg_counts;       // [nq, n_seg]; reset to 0 after reading
+  int n_seg;
+  int seg_cap;
+  int single_segment;        // fp32 validation kernel: one segment of n_seg * seg_cap slots, cursor in seg_counts[q,0]
+  int dense_count;           // > 0: prefix slots [0, dense_count) are all candidates (first launch), segments unused
   int k;
   // ---- outputs (nullable)
-  float* thresholds;         // [nq]
+  uint32_t* thr_ord;         // [nq] exact k-th best ranking value so far (order-preserving bits)
   float* out_scores;         // [nq, k]
   int32_t* out_ids;          // [nq, k]
   uint64_t* out_keys;        // [nq, k]
-  // ---- fused candidate exchange (nullable): peer_keys[s] is rank s's gathered buffer [world, nq, k]; this rank's
-  //      final keys are stored straight into slot `rank` of every peer's buffer over NVLink (P2P stores)
+  // ---- fused candidate exchange (nullable): peer_keys[s] is rank s's gathered buffer [world, nq_total, k]; this
+  //      rank's final keys are stored straight into slot `rank` of every peer's buffer over NVLink (P2P stores)
   uint64_t* const* peer_keys;
   int world;
   int rank;
-  int64_t nq_total;
+  int64_t nq_total;          // queries of the whole call (row stride of the peer buffers)
+  int64_t q_first;           // index of this batch's first query within the call (peer buffer row offset)
   int32_t* status;
 };
 }  // namespace ern

@@ -57,7 +57,7 @@ sim_f32_kernel(const float* __restrict__ Q, int64_t ldq, const float* __restrict
   for (int i = 0; i < 4; ++i) {
     const int64_t q = q0 + ty * 4 + i;
     if (q >= sink.nq) continue;
-    const float thr = sink.dense ? -INFINITY : sink.thresholds[q];
+    const float thr = sink.dense ? -INFINITY : ordered_to_f32(sink.thr_ord[q]);
     const int32_t excl = sink.exclude ? sink.exclude[q] : -1;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

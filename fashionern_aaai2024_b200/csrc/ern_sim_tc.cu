@@ -14,9 +14,15 @@
 // in a pair), warps 2..5 = epilogue; epilogue thread (quadrant, lane) owns one query row: it reads the
 // row's scores with tcgen05.ld (32 columns at a time), max-reduces them (FMNMX3) and only when the maximum reaches
 // the row's threshold walks a bit-mask of the 32 compares, appending survivors with a private cursor into the
-// list segment this work item owns (no atomics).  The epilogue is deliberately compact code (rolled chunk loop).
+// list segment this persistent unit owns for that query (no atomics).  A segment that is about to fill up is compacted
+// in place by its warp to its k best keys, which also tightens the query's threshold for every unit (see
+// CandidateSink): a launch is exact for any gallery order and any number of rows.
+// Work items are (super tile of `tiles_per_item` gallery tiles, query tile), super-tile-major, dealt round-robin to
+// the persistent units: the query tiles of a batch sweep the same few super tiles at the same time and share them
+// through L2.  The epilogue is deliberately compact code (rolled chunk loop).
 // Environment knobs (profiling aids, read once): ERN_FORCE_SINGLE_CTA=1, ERN_PREFETCH_TILES=n, ERN_DEBUG_FLAGS.
 #include "ern_common.cuh"
+#include "ern_compact.cuh"
 #include "ern_ptx.cuh"
 
 namespace ern {
@@ -41,8 +47,8 @@ struct Params {
   int num_kblocks;
   int n_qtiles;         // query tiles of (kPair ? 256 : 128) rows
   int tiles_total;      // gallery tiles of TILE_G rows in [row_begin, row_end)
-  int tiles_per_chunk;
-  int n_chunks;
+  int tiles_per_item;   // gallery tiles per work item (super tile)
+  int n_super;          // super tiles
   const uint8_t* gallery_base;  // non-null iff gallery rows are contiguous (ld == dim): enables the L2 prefetch
   int64_t gallery_rows;
   int row_bytes;
@@ -82,7 +88,7 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const bool leader = rank == 0;
   const int unit = kPair ? (blockIdx.x >> 1) : blockIdx.x;
   const int n_units = kPair ? (gridDim.x >> 1) : gridDim.x;
-  const int n_items = p.n_qtiles * p.n_chunks;
+  const int n_items = p.n_qtiles * p.n_super;
   int32_t* status = p.sink.status;
 
   if (threadIdx.x == 0) {
@@ -116,7 +122,7 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       uint32_t stage = 0, phase = 0, it = 0;
       for (int item = unit; item < n_items; item += n_units, ++it) {
         const int qt = item % p.n_qtiles;
-        const int chunk = item / p.n_qtiles;
+        const int st = item / p.n_qtiles;
         const int q_row = qt * (kBlockQ * kCta) + rank * kBlockQ;
         // A buffer is free once every MMA of the previous item has retired
         ptx::mbar_wait(ptx::smem_u32(&bars->a_empty), (it & 1) ^ 1, status, 1);
@@ -125,13 +131,12 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (kPair) ptx::tma_load_2d_pair(smem_a + kb * kTileBytes, &tmap_q, kb * kBlockK, q_row, a_full_dst);
           else       ptx::tma_load_2d(smem_a + kb * kTileBytes, &tmap_q, kb * kBlockK, q_row, a_full_dst);
         }
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
+        const int t0 = st * p.tiles_per_item;
+        const int t1 = min(t0 + p.tiles_per_item, p.tiles_total);
         for (int t = t0; t < t1; ++t) {
           const int g_row = static_cast<int>(p.sink.row_begin) + t * kTileG + rank * kBlockG;
-          // The query tiles of one chunk stream the same gallery tiles in lock-step, so whoever asks first waits
-          // for HBM and everybody else waits with it.  One unit per tile (rotating) pulls the tile into L2 a few
-          // tiles ahead, so the TMA loads of all of them find it there.
+          // (profiling knob, off by default) the query tiles of one super tile stream the same gallery tiles together:
+          // one unit per tile (rotating) pulls the tile into L2 a few tiles ahead of everybody's TMA loads.
           if (p.prefetch_tiles > 0 && leader && ((t + p.prefetch_tiles) % p.n_qtiles) == qt && t + p.prefetch_tiles < t1) {
             const int64_t prow = p.sink.row_begin + static_cast<int64_t>(t + p.prefetch_tiles) * kTileG;
             int64_t nrows = p.gallery_rows - prow;
@@ -157,11 +162,11 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockQ * kCta, kTileG);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, it = 0;
       for (int item = unit; item < n_items; item += n_units, ++it) {
-        const int chunk = item / p.n_qtiles;
+        const int st = item / p.n_qtiles;
         ptx::mbar_wait(ptx::smem_u32(&bars->a_full), it & 1, status, 3);
         ptx::tc_fence_after();
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
+        const int t0 = st * p.tiles_per_item;
+        const int t1 = min(t0 + p.tiles_per_item, p.tiles_total);
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1, status, 4);
           ptx::tc_fence_after();
@@ -195,18 +200,28 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const CandidateSink& sink = p.sink;
     for (int item = unit; item < n_items; item += n_units) {
       const int qt = item % p.n_qtiles;
-      const int chunk = item / p.n_qtiles;
+      const int st = item / p.n_qtiles;
       const int64_t q = static_cast<int64_t>(qt) * (kBlockQ * kCta) + rank * kBlockQ + row_in_tile;
       const bool q_ok = q < sink.nq;
       const bool dense = sink.dense != 0;
-      const float thr = q_ok ? (dense ? -INFINITY : sink.thresholds[q]) : INFINITY;
+      const bool live = q_ok && !dense;
       const int32_t excl = (q_ok && sink.exclude) ? sink.exclude[q] : -1;
-      // this thread is the only writer of segment `chunk` of query q: private cursor, plain stores
-      uint64_t* seg = sink.lists + (q_ok ? q : 0) * sink.cap + sink.keep + static_cast<int64_t>(chunk) * sink.seg_size;
-      int cnt = 0;
-      const int t0 = chunk * p.tiles_per_chunk;
-      const int t1 = min(t0 + p.tiles_per_chunk, p.tiles_total);
+      // this thread is the only writer of segment `unit` of query q: private cursor, plain stores
+      const int64_t qs = live ? q : 0;
+      uint64_t* seg = sink.segs + (qs * sink.n_seg + unit) * sink.seg_cap;
+      uint32_t* thr_ord_q = sink.thr_ord + qs;
+      int32_t* cnt_q = sink.seg_counts + qs * sink.n_seg + unit;
+      int cnt = live ? *cnt_q : 0;
+      float thr = INFINITY;                      // rows beyond the batch never append
+      const int full_at = sink.seg_cap - 32;      // a 32-column chunk appends at most 32 keys
+      const int t0 = st * p.tiles_per_item;
+      const int t1 = min(t0 + p.tiles_per_item, p.tiles_total);
       for (int t = t0; t < t1; ++t) {
+        // the query's lower bound may have been tightened by any unit since the last tile (stale is harmless)
+        if (live) {
+          const float g = ordered_to_f32(__ldcg(thr_ord_q));
+          thr = (t == t0) ? g : fmaxf(thr, g);
+        }
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase, status, 6);
         ptx::tc_fence_after();
         const int64_t g_base = sink.row_begin + static_cast<int64_t>(t) * kTileG;
@@ -253,11 +268,15 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                   const float r = rank_value<kRankBy>(__uint_as_float((j & 1) ? s2[1] : s2[0]));
                   const int64_t row = row0 + j;
                   const uint32_t gid = static_cast<uint32_t>(row + sink.id_offset);
-                  if (row < sink.row_end && q_ok && static_cast<int32_t>(gid) != excl) {
-                    if (cnt < sink.seg_size) seg[cnt] = make_key(r, gid);
-                    ++cnt;
-                  }
+                  if (row < sink.row_end && static_cast<int32_t>(gid) != excl) seg[cnt++] = make_key(r, gid);
                 }
+              }
+              // fewer than 32 free slots somewhere in the warp: those segments are reduced to their k best keys
+              const bool full = cnt > full_at;
+              if (__any_sync(0xffffffffu, full)) {
+                const CompactResult cr = warp_compact_segment(seg, cnt, thr, thr_ord_q, full, sink.k);
+                cnt = cr.cnt;
+                thr = cr.thr;
               }
             }
           }
@@ -271,9 +290,8 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      // publish how many candidates this work item left in its segment (may exceed seg_size: the selection
-      // kernel reports that as an overflow)
-      if (q_ok && !dense) sink.seg_counts[q * ERN_MAX_CHUNKS + chunk] = cnt;
+      // publish how many candidates this unit holds for the query
+      if (live) *cnt_q = cnt;
     }
   }
 
@@ -354,28 +372,27 @@ static int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const Params
   return ERN_OK;
 }
 
-// Pick the chunking of [row_begin,row_end) that minimises the modelled makespan: items = qtiles x chunks are
-// dealt round-robin to the persistent units; every item pays one extra tile-time to (re)load its query tile.
-static void plan_chunks(int n_qtiles, int tiles_total, int units, int max_chunks, int* n_chunks, int* tiles_per_chunk) {
-  long best_cost = -1;
-  int best_c = 1;
-  const int cmax = tiles_total < max_chunks ? tiles_total : max_chunks;
-  for (int c = 1; c <= cmax; ++c) {
-    const long tpc = (tiles_total + c - 1) / c;
-    const long real_c = (tiles_total + tpc - 1) / tpc;
-    const long rounds = (static_cast<long>(n_qtiles) * real_c + units - 1) / units;
-    const long cost = rounds * (tpc + 1);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best_c = static_cast<int>(real_c);
-    }
-  }
-  *tiles_per_chunk = (tiles_total + best_c - 1) / best_c;
-  *n_chunks = (tiles_total + *tiles_per_chunk - 1) / *tiles_per_chunk;
+// Tiles per work item.  Items = query tiles x super tiles, dealt round-robin: enough of them that the last round is a
+// small part of the launch (>= ~12 items per unit when the range allows), at most kMaxTilesPerItem so that a unit
+// re-loads a query tile (its only per-item cost, about half a tile time) no more often than once per 64 tiles.
+constexpr int kMaxTilesPerItem = 64;
+static int plan_tiles_per_item(int n_qtiles, int tiles_total, int units) {
+  static const int forced = [] { const char* e = getenv("ERN_TILES_PER_ITEM"); return e ? atoi(e) : 0; }();
+  if (forced > 0) return forced;
+  long tpi = static_cast<long>(tiles_total) * n_qtiles / (12L * units);
+  if (tpi < 1) tpi = 1;
+  if (tpi > kMaxTilesPerItem) tpi = kMaxTilesPerItem;
+  return static_cast<int>(tpi);
+}
+
+// persistent units (= candidate segments per query) the scoring kernel runs with for a batch of nq queries
+int units_for(int64_t nq, int force_single, int sm_count) {
+  const bool pair = !force_single && nq > kBlockQ;
+  return pair ? sm_count / 2 : sm_count;
 }
 
 // One launch of the tensor-core scoring kernel over shard rows [sink.row_begin, sink.row_end).
-int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, int dim, int rank_by,
+int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
            int force_single, int sm_count, const void* gallery, int64_t gallery_rows, int64_t ldg, cudaStream_t st) {
   const bool pair = !force_single && sink.nq > kBlockQ;
   const int tile_g = pair ? 256 : 128;
@@ -391,15 +408,12 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, CandidateSink& sink, in
   p.n_qtiles = cdiv(sink.nq, pair ? 2 * kBlockQ : kBlockQ);
   p.tiles_total = cdiv(sink.row_end - sink.row_begin, tile_g);
   if (p.tiles_total <= 0) return ERN_OK;
-  int units = pair ? sm_count / 2 : sm_count;
-  // on entry sink.n_chunks is the caller's upper bound on chunks (1 for the overflow-proof schedule)
-  const int max_chunks = sink.n_chunks > 0 && sink.n_chunks < ERN_MAX_CHUNKS ? sink.n_chunks : ERN_MAX_CHUNKS;
-  // (the selection kernel walks segments with one warp each; ERN_MAX_CHUNKS bounds the seg_counts row)
-  plan_chunks(p.n_qtiles, p.tiles_total, units, max_chunks, &p.n_chunks, &p.tiles_per_chunk);
-  sink.n_chunks = p.n_chunks;
-  sink.seg_size = (sink.cap - sink.keep) / p.n_chunks;
+  int units = units_for(sink.nq, force_single, sm_count);
+  ERN_REQUIRE(units <= sink.n_seg, "internal: %d scoring units but %d candidate segments per query", units, sink.n_seg);
+  p.tiles_per_item = plan_tiles_per_item(p.n_qtiles, p.tiles_total, units);
+  p.n_super = cdiv(p.tiles_total, p.tiles_per_item);
   p.sink = sink;
-  const long items = static_cast<long>(p.n_qtiles) * p.n_chunks;
+  const long items = static_cast<long>(p.n_qtiles) * p.n_super;
   if (items < units) units = static_cast<int>(items);
   const int grid = pair ? 2 * units : units;
   if (pair) {

@@ -38,57 +38,77 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
   __shared__ uint64_t keys[ERN_SORT_CAP];
   __shared__ uint64_t top[kSmallSort];
   __shared__ int hist[256];
-  __shared__ int n_shared, m_shared, remaining_sh;
-  __shared__ uint32_t prefix_sh;
+  __shared__ int n_shared, m_shared, remaining_sh, ge_sh;
+  __shared__ uint64_t prefix_sh;
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
   const int k = p.k;
+  // (read before the kernel's last step overwrites it; dense launches and merges have no bound yet)
+  const uint32_t thr_floor = (p.n_lists == 0 && p.dense_count == 0 && p.thr_ord) ? p.thr_ord[q] : 0u;
   if (tid == 0) {
     n_shared = 0;
     m_shared = 0;
     remaining_sh = k;
     prefix_sh = 0;
+    ge_sh = 0;
   }
   __syncthreads();
 
-  // ---- gather the non-empty candidates densely into shared memory (order is irrelevant) ----------------
-  auto push = [&](uint64_t key) {
-    if (key != 0ull) {
-      const int pos = atomicAdd(&n_shared, 1);
-      if (pos < ERN_SORT_CAP) keys[pos] = key;
+  // ---- every non-empty candidate key of this query, straight from its sources (order is irrelevant) ------------
+  auto scan_sources = [&](auto&& f) {
+    if (p.n_lists > 0) {
+      const int total = p.n_lists * p.k_in;
+      for (int i = tid; i < total; i += kSelectThreads) {
+        const uint64_t key = p.merge_src[(i / p.k_in) * p.list_stride + q * p.query_stride + (i % p.k_in)];
+        if (key) f(key);
+      }
+      return;
+    }
+    const uint64_t* pre = p.prefix + q * ERN_DENSE_ROWS;
+    const int np = p.dense_count > 0 ? p.dense_count : p.prev_counts[q];
+    // keys below the query's current lower bound (tightened inside the scoring launch) cannot be among the k best
+    const uint64_t floor_key = static_cast<uint64_t>(thr_floor) << 32;
+    for (int i = tid; i < np; i += kSelectThreads) {
+      const uint64_t key = pre[i];
+      if (key && key >= floor_key) f(key);
+    }
+    if (p.dense_count > 0) return;
+    const int32_t* sc = p.seg_counts + q * p.n_seg;
+    const uint64_t* segs = p.segs + q * static_cast<int64_t>(p.n_seg) * p.seg_cap;
+    if (p.single_segment) {
+      const int cnt = min(sc[0], p.n_seg * p.seg_cap);
+      for (int i = tid; i < cnt; i += kSelectThreads) {
+        const uint64_t key = segs[i];
+        if (key >= floor_key) f(key);
+      }
+    } else {
+      // one warp per segment: coalesced reads of exactly the published entries
+      for (int u = tid >> 5; u < p.n_seg; u += kSelectThreads / 32) {
+        const int cnt = min(sc[u], p.seg_cap);
+        const uint64_t* seg = segs + static_cast<int64_t>(u) * p.seg_cap;
+        for (int i = tid & 31; i < cnt; i += 32) {
+          const uint64_t key = seg[i];
+          if (key >= floor_key) f(key);
+        }
+      }
     }
   };
-  if (p.n_lists > 0) {
-    const int total = p.n_lists * p.k_in;
-    for (int i = tid; i < total; i += kSelectThreads)
-      push(p.merge_src[(i / p.k_in) * p.list_stride + q * p.query_stride + (i % p.k_in)]);
-  } else {
-    const uint64_t* list = p.lists + q * p.cap;
-    if (p.dense_count > 0) {
-      for (int i = tid; i < p.dense_count; i += kSelectThreads) push(list[i]);
-    } else {
-      const int prev = p.prev_counts[q];
-      for (int i = tid; i < prev; i += kSelectThreads) push(list[i]);
-      int32_t* sc = p.seg_counts + q * ERN_MAX_CHUNKS;
-      // one warp per segment: coalesced reads of exactly the published entries
-      for (int c = tid >> 5; c < p.n_chunks; c += kSelectThreads / 32) {
-        const int cnt = min(sc[c], p.seg_size);
-        const uint64_t* seg = list + p.keep + c * p.seg_size;
-        for (int i = tid & 31; i < cnt; i += 32) push(seg[i]);
-      }
-      __syncthreads();
-      if (tid < p.n_chunks) {
-        if (sc[tid] > p.seg_size && p.status) atomicAdd(&p.status[0], 1);   // a segment overflowed: not exact
-        sc[tid] = 0;
-      }
-    }
-  }
+
+  // ---- count them; up to ERN_SORT_CAP are staged in shared memory (the usual case: all of them) ------------------
+  scan_sources([&](uint64_t key) {
+    const int pos = atomicAdd(&n_shared, 1);
+    if (pos < ERN_SORT_CAP) keys[pos] = key;
+  });
   __syncthreads();
-  int n = n_shared;
-  if (n > ERN_SORT_CAP) {
-    if (tid == 0 && p.status) atomicAdd(&p.status[0], 1);
-    n = ERN_SORT_CAP;
-  }
+  const int n = n_shared;
+  const bool staged = n <= ERN_SORT_CAP;
+  auto scan = [&](auto&& f) {
+    if (staged) {
+      for (int i = tid; i < n; i += kSelectThreads) f(keys[i]);
+    } else {
+      scan_sources(f);        // adversarially ordered galleries only: candidates are re-read from L2 per pass
+    }
+  };
 
   const uint64_t* sorted = keys;   // array whose first min(n,k) entries are the answer, descending
   int sorted_len = 0;
@@ -99,17 +119,17 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
     bitonic_sort_desc(keys, pow2, tid);
     sorted_len = pow2;
   } else {
-    // ---- radix select (4 x 8 bits, MSB first) of the k-th largest 32-bit ranking value, then sort only the
-    //      candidates that reach it.  Ties at the threshold are all kept, so the result stays exact.
-    uint32_t mask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    // ---- radix select (8 bits per pass, MSB first) of the k-th largest key.  After the four passes over the
+    //      ranking value it stops as soon as at most kSmallSort candidates reach the k-th value (ties included, so
+    //      the result stays exact); otherwise the id half is resolved too and exactly k candidates remain.
+    uint64_t mask = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
       hist[tid] = 0;
       __syncthreads();
-      const uint32_t prefix = prefix_sh;
-      for (int i = tid; i < n; i += kSelectThreads) {
-        const uint32_t h = static_cast<uint32_t>(keys[i] >> 32);
-        if ((h & mask) == prefix) atomicAdd(&hist[(h >> shift) & 255u], 1);
-      }
+      const uint64_t prefix = prefix_sh;
+      scan([&](uint64_t key) {
+        if ((key & mask) == prefix) atomicAdd(&hist[static_cast<int>((key >> shift) & 255u)], 1);
+      });
       __syncthreads();
       if (tid < 32) {
         int c[8], sum = 0;
@@ -132,8 +152,9 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
 #pragma unroll
           for (int j = 7; j >= 0; --j) {
             if (above < remaining && remaining <= above + c[j]) {
-              prefix_sh = prefix | (static_cast<uint32_t>(tid * 8 + j) << shift);
+              prefix_sh = prefix | (static_cast<uint64_t>(tid * 8 + j) << shift);
               remaining_sh = remaining - above;
+              ge_sh = (k - (remaining - above)) + c[j];   // candidates >= the prefix found so far
               above = 1 << 30;   // found; stop matching
             } else if (above < (1 << 30)) {
               above += c[j];
@@ -141,52 +162,58 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
           }
         }
       }
-      mask |= 0xFFu << shift;
+      mask |= static_cast<uint64_t>(0xFFu) << shift;
       __syncthreads();
+      if (shift == 32 && ge_sh <= kSmallSort) break;
     }
-    const uint32_t thr32 = prefix_sh;
-    for (int i = tid; i < n; i += kSelectThreads) {
-      const uint64_t key = keys[i];
-      if (static_cast<uint32_t>(key >> 32) >= thr32) {
+    const uint64_t thr64 = prefix_sh;
+    scan([&](uint64_t key) {
+      if (key >= thr64) {
         const int pos = atomicAdd(&m_shared, 1);
         if (pos < kSmallSort) top[pos] = key;
       }
-    }
+    });
     __syncthreads();
-    const int m = m_shared;
-    if (m <= kSmallSort) {
-      int pow2 = 32;
-      while (pow2 < m) pow2 <<= 1;
-      for (int i = m + tid; i < pow2; i += kSelectThreads) top[i] = 0ull;
-      bitonic_sort_desc(top, pow2, tid);
-      sorted = top;
-      sorted_len = pow2;
-    } else {
-      // more than kSmallSort candidates tie at the threshold value: sort everything
-      int pow2 = 32;
-      while (pow2 < n) pow2 <<= 1;
-      for (int i = n + tid; i < pow2; i += kSelectThreads) keys[i] = 0ull;
-      bitonic_sort_desc(keys, pow2, tid);
-      sorted_len = pow2;
+    int m = m_shared;
+    if (m > kSmallSort) {        // only possible with duplicated keys (never produced by the scoring kernels)
+      if (tid == 0 && p.status) atomicAdd(&p.status[0], 1);
+      m = kSmallSort;
     }
+    int pow2 = 32;
+    while (pow2 < m) pow2 <<= 1;
+    for (int i = m + tid; i < pow2; i += kSelectThreads) top[i] = 0ull;
+    bitonic_sort_desc(top, pow2, tid);
+    sorted = top;
+    sorted_len = pow2;
   }
 
   for (int j = tid; j < k; j += kSelectThreads) {
     const uint64_t key = (j < sorted_len) ? sorted[j] : 0ull;
-    if (p.lists) p.lists[q * p.cap + j] = key;
+    if (p.prefix) p.prefix[q * ERN_DENSE_ROWS + j] = key;
     if (p.out_keys) p.out_keys[q * k + j] = key;
     if (p.peer_keys) {
-      const int64_t slot = (static_cast<int64_t>(p.rank) * p.nq_total + q) * k + j;
+      const int64_t slot = (static_cast<int64_t>(p.rank) * p.nq_total + p.q_first + q) * k + j;
       for (int s = 0; s < p.world; ++s) p.peer_keys[s][slot] = key;
     }
     if (p.out_scores) p.out_scores[q * k + j] = key ? key_value(key) : -INFINITY;
     if (p.out_ids) p.out_ids[q * k + j] = key ? key_id(key) : -1;
   }
+  // every pass over the sources is done (the sorts above end with a block barrier): reset the segment cursors
+  if (p.n_lists == 0 && p.dense_count == 0) {
+    if (p.single_segment) {
+      if (tid == 0) {
+        if (p.seg_counts[q * p.n_seg] > p.n_seg * p.seg_cap && p.status) atomicAdd(&p.status[0], 1);  // cannot happen
+        p.seg_counts[q * p.n_seg] = 0;
+      }
+    } else {
+      for (int u = tid; u < p.n_seg; u += kSelectThreads) p.seg_counts[q * p.n_seg + u] = 0;
+    }
+  }
   if (tid == 0) {
     const uint64_t kth = (k - 1 < sorted_len) ? sorted[k - 1] : 0ull;
     if (p.prev_counts) p.prev_counts[q] = n < k ? n : k;
     // fewer than k real candidates so far: no lower bound yet
-    if (p.thresholds) p.thresholds[q] = kth ? key_value(kth) : -INFINITY;
+    if (p.thr_ord) p.thr_ord[q] = kth ? static_cast<uint32_t>(kth >> 32) : f32_to_ordered(-INFINITY);
   }
 }
 
@@ -197,20 +224,21 @@ int launch_select(const SelectParams& p, int64_t nq, cudaStream_t st) {
   return ERN_OK;
 }
 
-__global__ void init_state_kernel(int32_t* prev_counts, int32_t* seg_counts, float* thr, int64_t nq, int32_t* status) {
+__global__ void init_state_kernel(int32_t* prev_counts, int32_t* seg_counts, uint32_t* thr_ord, int64_t nq, int n_seg,
+                                  int32_t* status) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < nq) {
     prev_counts[i] = 0;
-    thr[i] = -INFINITY;
+    thr_ord[i] = f32_to_ordered(-INFINITY);
   }
-  if (i < nq * ERN_MAX_CHUNKS) seg_counts[i] = 0;
+  if (i < nq * n_seg) seg_counts[i] = 0;
   if (i < 4 && status) status[i] = 0;
 }
 
-int launch_init_state(int32_t* prev_counts, int32_t* seg_counts, float* thr, int64_t nq, int32_t* status,
-                      cudaStream_t st) {
-  const int64_t n = nq * ERN_MAX_CHUNKS < 4 ? 4 : nq * ERN_MAX_CHUNKS;
-  init_state_kernel<<<cdiv(n, 256), 256, 0, st>>>(prev_counts, seg_counts, thr, nq, status);
+int launch_init_state(int32_t* prev_counts, int32_t* seg_counts, uint32_t* thr_ord, int64_t nq, int n_seg,
+                      int32_t* status, cudaStream_t st) {
+  const int64_t n = nq * n_seg < 4 ? 4 : nq * n_seg;
+  init_state_kernel<<<cdiv(n, 256), 256, 0, st>>>(prev_counts, seg_counts, thr_ord, nq, n_seg, status);
   ERN_CUDA(cudaGetLastError());
   return ERN_OK;
 }

@@ -11,7 +11,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, PHASE_MAX_ROWS, RANK_REFERENCE,
+from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, QUERY_BATCH, RANK_REFERENCE,
                    RANK_SIMILARITY, SORT_CAP, ErnError)
 
 __all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "gather_scores",
@@ -61,13 +61,34 @@ def l2norm_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, 
     return of, ob
 
 
-def _phase_count(n_rows: int, k: int, growth: int) -> int:
-    """Number of scoring launches ern_sim_topk issues (mirrors the schedule in csrc/ern_capi.cu)."""
+def _phase_count(n_rows: int, k: int, growth: int, max_rows_per_launch: Optional[int] = None) -> int:
+    """Number of scoring launches ern_sim_topk issues per query batch (mirrors the schedule in csrc/ern_capi.cu):
+    rows [0,256) densely, then [b, growth*b) -- the fp32 validation kernel additionally caps a launch at the
+    number of candidate slots a query owns (``max_rows_per_launch``)."""
     n, begin = 1, min(n_rows, DENSE_ROWS)
     while begin < n_rows:
-        begin = begin + (SORT_CAP - k) if growth == 1 else min(begin * growth, begin + PHASE_MAX_ROWS)
+        end = begin + (SORT_CAP - k) if growth == 1 else begin * growth
+        if max_rows_per_launch is not None:
+            end = min(end, begin + max_rows_per_launch)
+        begin = end
         n += 1
     return n
+
+
+def _sim_launches(nq: int, n_rows: int, k: int, growth: int, mode: int, device) -> int:
+    """Kernel launches of one ern_sim_topk call: per query batch one state-init launch plus a scoring and a
+    selection launch per schedule step."""
+    if nq == 0:
+        return 0
+    total = 0
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    for q0 in range(0, nq, QUERY_BATCH):
+        bq = min(QUERY_BATCH, nq - q0)
+        cap = None
+        if mode == MODE_FP32:
+            cap = (sms // 2 if bq > 128 else sms) * (128 if k <= 64 else 256)
+        total += 1 + 2 * _phase_count(n_rows, k, growth, cap)
+    return total
 
 
 def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int = MODE_BF16,
@@ -77,8 +98,9 @@ def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int 
     (run/test/test_fiq.py:49-50) without materialising the [Q,N] matrix.
 
     Returns ``(values fp32 [Q,k], ids int32 [Q,k], keys uint64-as-int64 [Q,k] | None, status int32[4])``.
-    ``check_overflow=True`` reads ``status`` back (one host sync) and transparently re-runs with the
-    overflow-proof schedule if a candidate list overflowed; with ``False`` the caller must inspect it.
+    The result is exact for any gallery order (candidate segments compact themselves inside the kernel), so there
+    is no fallback path: ``status[0]`` can only be non-zero on an internal inconsistency, and
+    ``check_overflow=True`` (one host sync) turns that into an ``ErnError``.
     """
     q = _rowmajor(queries, "queries")
     g = _rowmajor(gallery, "gallery")
@@ -105,21 +127,16 @@ def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int 
         wsb = lib.ern_sim_topk_workspace_bytes(nq, dim, mode)
         ws = _workspace(wsb, dev)
 
-        def run(gr):
-            L.check(lib.ern_sim_topk(q.data_ptr(), nq, q.stride(0), g.data_ptr(), n_rows, g.stride(0), dim, dtype,
-                                     int(id_offset), L.ptr(exclude_ids), int(k), mode, rank_by, gr,
-                                     vals.data_ptr(), ids.data_ptr(), L.ptr(keys), status.data_ptr(),
-                                     ws.data_ptr(), wsb, L.stream_ptr(dev)))
-            launch_counter.add(1 + 2 * _phase_count(n_rows, k, gr) if nq else 0)
-
         if nq == 0:
             status.zero_()
             return vals, ids, keys, status
-        run(growth)
-        if check_overflow and nq and int(status[0].item()) != 0:
-            run(1)
-            if int(status[0].item()) != 0:
-                raise ErnError("candidate list overflow even with the conservative schedule (internal error)")
+        L.check(lib.ern_sim_topk(q.data_ptr(), nq, q.stride(0), g.data_ptr(), n_rows, g.stride(0), dim, dtype,
+                                 int(id_offset), L.ptr(exclude_ids), int(k), mode, rank_by, growth,
+                                 vals.data_ptr(), ids.data_ptr(), L.ptr(keys), status.data_ptr(),
+                                 ws.data_ptr(), wsb, L.stream_ptr(dev)))
+        launch_counter.add(_sim_launches(nq, n_rows, k, growth, mode, dev))
+        if check_overflow and int(status[0].item()) != 0:
+            raise ErnError(f"ern_sim_topk reported an inconsistent candidate store (status {status.tolist()})")
     return vals, ids, keys, status
 
 
@@ -147,7 +164,7 @@ def sim_topk_exchange(queries: torch.Tensor, gallery: torch.Tensor, k: int, peer
                                           DTYPE_F32 if mode == MODE_FP32 else DTYPE_BF16, int(id_offset),
                                           L.ptr(exclude_ids), int(k), mode, rank_by, growth, peer_ptrs_dev, world,
                                           rank, status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev)))
-        launch_counter.add(1 + 2 * _phase_count(g.shape[0], k, growth))
+        launch_counter.add(_sim_launches(nq, g.shape[0], k, growth, mode, dev))
     return status
 
 

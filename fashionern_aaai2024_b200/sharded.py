@@ -96,10 +96,8 @@ def sharded_topk(queries: torch.Tensor, local_gallery: torch.Tensor, k: int, id_
         pb.turn ^= 1
         status = ops.sim_topk_exchange(queries, local_gallery, k, hdl.buffer_ptrs_dev, pb.world, hdl.rank, mode=mode,
                                        rank_by=rank_by, exclude_ids=exclude_ids, id_offset=id_offset)
-        if check_overflow and int(status[0].item()) != 0:          # pathological ordering: exact fallback
-            status = ops.sim_topk_exchange(queries, local_gallery, k, hdl.buffer_ptrs_dev, pb.world, hdl.rank,
-                                           mode=mode, rank_by=rank_by, exclude_ids=exclude_ids, id_offset=id_offset,
-                                           growth=1)
+        if check_overflow and int(status[0].item()) != 0:
+            raise ops.ErnError(f"ern_sim_topk_exchange reported an inconsistent candidate store ({status.tolist()})")
         hdl.barrier(channel=0)                                      # every rank's stores have landed everywhere
         return (*ops.topk_merge(buf, k), status)
     _, _, keys, status = ops.sim_topk(queries, local_gallery, k, mode=mode, rank_by=rank_by, exclude_ids=exclude_ids,

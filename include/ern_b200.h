@@ -54,19 +54,15 @@ extern "C" {
 #define ERN_RANK_REFERENCE 1  /* -(1 - s) rounded in fp32: the reference's `1 - pred @ index.T`    */
                               /* (run/test/test_fiq.py:49) with its rounding-induced ties          */
 
-/* max k of the streaming top-k; slots of one query's candidate list (x4 for batches of <= 1024 queries, which
- * need more, smaller gallery chunks to fill the GPU); max candidates one selection/merge pass can take; max
- * gallery chunks (= independent writers) per query and launch */
+/* max k of the streaming top-k; slots of one candidate segment (one per query and persistent scoring unit; 128 when
+ * k <= 64); max candidates the selection/merge kernel stages in shared memory (more are handled from L2); queries that
+ * go through the launch schedule together (larger batches are processed ERN_QUERY_BATCH at a time) */
 #define ERN_MAX_K 128
-#define ERN_LIST_CAP 4096
+#define ERN_SEG_CAP 256
 #define ERN_SORT_CAP 2048
-#define ERN_MAX_CHUNKS 256
-/* gallery rows scored densely (every score kept) before thresholds exist */
+#define ERN_QUERY_BATCH 4096
+/* gallery rows scored densely (every score kept) before thresholds exist; also the slots of a query's prefix list */
 #define ERN_DENSE_ROWS 256
-/* most gallery rows one scoring launch covers: the query tiles of a batch sweep each gallery chunk together and share
- * it through L2; a chunk longer than ~500 tiles lets them drift apart (measured: 3.0x the gallery bytes from DRAM on a
- * 58.7M-row launch against 1.2x on a 7.3M-row one), so long ranges are cut into launches of at most this many rows */
-#define ERN_PHASE_MAX_ROWS 8388608
 
 ERN_API int ern_version(void);
 ERN_API const char* ern_last_error(void);
@@ -196,10 +192,12 @@ ERN_API int ern_dvr_encode(const ern_dvr_weights* w, int dim, int heads, int pat
  *   out_ids    [nq,k] int32 global ids, ties -> lower id first; missing entries: score -inf, id -1
  *   out_keys   (nullable) [nq,k] uint64 sortable (value,id) keys, the wire format of the multi-GPU
  *             candidate exchange (ern_topk_merge)
- *   growth    gallery-range growth factor of the threshold schedule (>=2; 8 is the default);
- *             growth == 1 selects the overflow-proof conservative schedule
- *   status_dev int32[4]: [0] != 0 => a candidate list overflowed (pathologically ordered gallery):
- *             results are NOT exact, call again with growth = 1.
+ *   growth    gallery-range growth factor of the launch schedule (>=2; 8 is the default): launch i covers rows
+ *             [b, growth*b) starting from the exact k-th best of rows [0,b) as each query's threshold.  It is a cost
+ *             knob only: candidate segments compact themselves inside the kernel, so the result is exact for ANY
+ *             gallery order and any growth (growth == 1: fixed 1920-row steps, a test hook).
+ *   status_dev int32[4]: [0] != 0 => internal error (candidate storage inconsistent; never expected);
+ *             [1..3] mbarrier watchdog diagnostics of a trapped launch.
  * MODE_BF16 requires dim % 64 == 0, dim <= 768 and 16-byte aligned rows.
  * ------------------------------------------------------------------------------------------- */
 ERN_API size_t ern_sim_topk_workspace_bytes(int64_t nq, int dim, int mode);

@@ -33,11 +33,15 @@ def test_version_and_constants():
     with open(os.path.join(ROOT, "include", "ern_b200.h")) as f:
         src = f.read()
     assert int(re.search(r"#define ERN_MAX_K (\d+)", src).group(1)) == _lib.MAX_K
-    assert int(re.search(r"#define ERN_LIST_CAP (\d+)", src).group(1)) == _lib.LIST_CAP
+    assert int(re.search(r"#define ERN_SEG_CAP (\d+)", src).group(1)) == _lib.SEG_CAP
     assert int(re.search(r"#define ERN_SORT_CAP (\d+)", src).group(1)) == _lib.SORT_CAP
     assert int(re.search(r"#define ERN_DENSE_ROWS (\d+)", src).group(1)) == _lib.DENSE_ROWS
-    assert int(re.search(r"#define ERN_PHASE_MAX_ROWS (\d+)", src).group(1)) == _lib.PHASE_MAX_ROWS
-    assert lib.ern_sim_topk_workspace_bytes(4096, 640, 0) >= 4096 * _lib.LIST_CAP * 8
+    assert int(re.search(r"#define ERN_QUERY_BATCH (\d+)", src).group(1)) == _lib.QUERY_BATCH
+    # candidate storage of one query batch: a 256-slot prefix + one 256-slot segment per CTA pair (74 on a B200)
+    one_batch = lib.ern_sim_topk_workspace_bytes(4096, 640, 0)
+    assert one_batch >= 4096 * (_lib.DENSE_ROWS + 74 * _lib.SEG_CAP) * 8
+    # larger calls are processed one batch at a time in the same storage
+    assert lib.ern_sim_topk_workspace_bytes(33480, 640, 0) == one_batch
     assert lib.ern_combiner_packed_bytes(640) >= (8 * 640 * 640 + 64 * 640 * 640) * 2
 
 
