@@ -14,12 +14,13 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libern_b200.so")
+# ERN_B200_LIB: load another build of the same C ABI (A/B timing of two builds in one GPU session); default in-tree
+LIB_PATH = os.environ.get("ERN_B200_LIB") or os.path.join(_HERE, "libern_b200.so")
 
 MODE_BF16, MODE_FP32 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 RANK_SIMILARITY, RANK_REFERENCE = 0, 1
-MAX_K, SEG_CAP, SORT_CAP, QUERY_BATCH, DENSE_ROWS = 128, 256, 2048, 4096, 256
+MAX_K, SEG_CAP, SORT_CAP, QUERY_BATCH, DENSE_ROWS = 128, 512, 2048, 4096, 256
 
 # every symbol include/ern_b200.h declares; tests check the .so exports exactly these
 SYMBOLS = (

@@ -75,8 +75,8 @@ static SimWorkspace carve_sim(void* base, int64_t batch, int n_seg, int seg_cap)
   w.bytes = off;
   return w;
 }
-// slots per segment: room for k survivors plus at least 64 appends between two in-kernel compactions
-static int seg_cap_for(int k) { return k <= 64 ? 128 : ERN_SEG_CAP; }
+// slots per segment: the survivors of a pruning pass (<= 256) plus every score of one 256-row gallery tile
+static int seg_cap_for(int k) { (void)k; return ERN_SEG_CAP; }
 
 // test hook: ERN_FORCE_SINGLE_CTA=1 makes the tensor-core path use the 1-CTA kernel even for large batches
 static int force_single() {

@@ -41,6 +41,7 @@ constexpr int kThreads = 192;
 constexpr int kProducerWarp = 4;
 constexpr int kMmaWarp = 5;
 constexpr int kSmemBytes = 1024 + kTotalTiles * kTileBytes + 512;
+constexpr int kDenseAppendFrom = 7;  // survivors in one 32-column chunk above which the unrolled append path is taken
 
 struct Params {
   CandidateSink sink;
@@ -54,7 +55,33 @@ struct Params {
   int row_bytes;
   int prefetch_tiles;   // how many gallery tiles ahead of the TMA loads the L2 prefetch runs (0 = off)
   int debug;            // profiling aid (ERN_DEBUG_FLAGS): 1 = never take the append path, 2 = skip the TMEM reads
+  unsigned long long* trace;   // profiling aid (ERN_TRACE_PTR): per unit 8 counters, see tools/trace_sim.py; null = off
 };
+
+// One 32-column chunk of scores, passed BY VALUE to the out-of-line burst path so that the hot loop's register
+// allocation does not see it (the copy to the callee's frame only happens on the rare path).
+struct Chunk32 {
+  uint32_t v[32];
+};
+template <int kRankBy>
+static __device__ __noinline__ int dense_append(uint64_t* seg, int cnt, uint32_t mask, Chunk32 ch, int64_t row0,
+                                                int64_t row_end, int64_t id_offset, int32_t excl) {
+  // rows past the end of the range and the excluded id leave the mask first, then every survivor's slot follows from a
+  // prefix popcount of the mask: 32 independent predicated stores, no cursor dependency chain (this warp is alone on
+  // its scheduler, so a serial chain would run at instruction latency, not issue rate)
+  const int64_t left = row_end - row0;                       // rows of this chunk inside the range (ragged last tile)
+  if (left <= 0) mask = 0u;
+  else if (left < 32) mask &= (1u << left) - 1u;
+  const int64_t ex = static_cast<int64_t>(excl) - id_offset - row0;
+  if (excl >= 0 && ex >= 0 && ex < 32) mask &= ~(1u << ex);
+  const uint32_t gid0 = static_cast<uint32_t>(row0 + id_offset);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if ((mask >> j) & 1u)
+      seg[cnt + __popc(mask & ((1u << j) - 1u))] = make_key(rank_value<kRankBy>(__uint_as_float(ch.v[j])), gid0 + j);
+  }
+  return cnt + __popc(mask);
+}
 
 struct Barriers {
   uint64_t full[kMaxStages];
@@ -161,18 +188,36 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     if (leader && lane == 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockQ * kCta, kTileG);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, it = 0;
+      // cycle accounting of the issuing thread (ERN_TRACE_PTR): total cycles and tiles cost nothing inside the loop;
+      // the per-wait split perturbs the issue loop by ~8 % and is compiled in only with -DERN_SIM_TRACE_WAITS
+      const bool tr = p.trace != nullptr;
+      const long long c_begin = tr ? clock64() : 0;
+      long long n_tiles = 0;
+#ifdef ERN_SIM_TRACE_WAITS
+      long long w_full = 0, w_acc = 0, w_a = 0, c0 = 0;
+#define ERN_TW(x) x
+#else
+#define ERN_TW(x)
+#endif
       for (int item = unit; item < n_items; item += n_units, ++it) {
         const int st = item / p.n_qtiles;
+        ERN_TW(c0 = clock64();)
         ptx::mbar_wait(ptx::smem_u32(&bars->a_full), it & 1, status, 3);
+        ERN_TW(w_a += clock64() - c0;)
         ptx::tc_fence_after();
         const int t0 = st * p.tiles_per_item;
         const int t1 = min(t0 + p.tiles_per_item, p.tiles_total);
+        n_tiles += t1 - t0;
         for (int t = t0; t < t1; ++t) {
+          ERN_TW(c0 = clock64();)
           ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1, status, 4);
+          ERN_TW(w_acc += clock64() - c0;)
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * kAccCols;
           for (int kb = 0; kb < p.num_kblocks; ++kb) {
+            ERN_TW(c0 = clock64();)
             ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase, status, 5);
+            ERN_TW(w_full += clock64() - c0;)
             ptx::tc_fence_after();
             const uint64_t adesc = ptx::smem_desc_sw128(smem_a + kb * kTileBytes);
             const uint64_t bdesc = ptx::smem_desc_sw128(smem_b + stage * kTileBytes);
@@ -189,6 +234,16 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         }
         ptx::umma_commit<kCta>(ptx::smem_u32(&bars->a_empty));
       }
+      if (tr) {
+        unsigned long long* o = p.trace + static_cast<size_t>(unit) * 8;
+        o[0] += static_cast<unsigned long long>(clock64() - c_begin);
+        o[1] += static_cast<unsigned long long>(n_tiles);
+#ifdef ERN_SIM_TRACE_WAITS
+        o[2] += static_cast<unsigned long long>(w_full);
+        o[3] += static_cast<unsigned long long>(w_acc);
+        o[4] += static_cast<unsigned long long>(w_a);
+#endif
+      }
     }
     __syncwarp();
   } else {
@@ -198,6 +253,10 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t empty_dst_base = ptx::smem_u32(&bars->tmem_empty[0]);
     uint32_t acc = 0, acc_phase = 0;
     const CandidateSink& sink = p.sink;
+#ifdef ERN_SIM_TRACE_WAITS
+    const bool etr = p.trace != nullptr && leader && warp == 0 && lane == 0;   // one epilogue warp of the leader CTA
+    long long e_begin = etr ? clock64() : 0, e_wait = 0, ec0 = 0, ec1 = 0, e_comp = 0, n_comp = 0, n_t4 = 0, n_t8 = 0, n_t16 = 0, e_tmax = 0;
+#endif
     for (int item = unit; item < n_items; item += n_units) {
       const int qt = item % p.n_qtiles;
       const int st = item / p.n_qtiles;
@@ -213,7 +272,11 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       int32_t* cnt_q = sink.seg_counts + qs * sink.n_seg + unit;
       int cnt = live ? *cnt_q : 0;
       float thr = INFINITY;                      // rows beyond the batch never append
-      const int full_at = sink.seg_cap - 32;      // a 32-column chunk appends at most 32 keys
+      // A tile appends at most kTileG keys to a segment, so a segment that holds no more than `prune_at` keys when a
+      // tile starts cannot overflow; it is pruned (warp_compact_segment) AFTER the tile's accumulator has been handed
+      // back, i.e. in the time this warp would otherwise spend waiting for the next tile's MMAs.
+      const int prune_at = sink.seg_cap - kTileG;
+      const int keep_max = sink.k + (prune_at - sink.k) / 4;   // a pruning pass leaves between k and keep_max keys
       const int t0 = st * p.tiles_per_item;
       const int t1 = min(t0 + p.tiles_per_item, p.tiles_total);
       for (int t = t0; t < t1; ++t) {
@@ -222,7 +285,9 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           const float g = ordered_to_f32(__ldcg(thr_ord_q));
           thr = (t == t0) ? g : fmaxf(thr, g);
         }
+        ERN_TW(if (etr) ec0 = clock64();)
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase, status, 6);
+        ERN_TW(if (etr) { e_wait += clock64() - ec0; ec1 = clock64(); })
         ptx::tc_fence_after();
         const int64_t g_base = sink.row_begin + static_cast<int64_t>(t) * kTileG;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols;
@@ -252,6 +317,15 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   mask |= (rank_value<kRankBy>(__uint_as_float(v[j])) >= thr ? 1u : 0u) << j;
+                if (__popc(mask) > kDenseAppendFrom) {
+                  // a burst (ordered gallery: a cluster of rows close to this query): out-of-line straight-line
+                  // appends, ~8 instructions per column instead of the ~50 of a select-tree walk step
+                  Chunk32 ch;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) ch.v[j] = v[j];
+                  cnt = dense_append<kRankBy>(seg, cnt, mask, ch, row0, sink.row_end, sink.id_offset, excl);
+                  mask = 0;
+                }
                 while (mask) {
                   const int j = __ffs(mask) - 1;
                   mask &= mask - 1;
@@ -271,28 +345,43 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                   if (row < sink.row_end && static_cast<int32_t>(gid) != excl) seg[cnt++] = make_key(r, gid);
                 }
               }
-              // fewer than 32 free slots somewhere in the warp: those segments are reduced to their k best keys
-              const bool full = cnt > full_at;
-              if (__any_sync(0xffffffffu, full)) {
-                const CompactResult cr = warp_compact_segment(seg, cnt, thr, thr_ord_q, full, sink.k);
-                cnt = cr.cnt;
-                thr = cr.thr;
-              }
             }
           }
         }
         // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
         ptx::tc_fence_before();
         __syncwarp();
+        ERN_TW(if (etr) { const long long d = clock64() - ec1; if (d > 4000) ++n_t4; if (d > 8000) ++n_t8; if (d > 16000) ++n_t16; if (d > e_tmax) e_tmax = d; })
         if (lane == 0) {
           const uint32_t dst = empty_dst_base + acc * 8;
           if (kPair) ptx::mbar_arrive_cluster(ptx::mapa(dst, 0)); else ptx::mbar_arrive(dst);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        // segments that could not take another whole tile are pruned to their best keys now
+        const bool full = cnt > prune_at;
+        if (__any_sync(0xffffffffu, full)) {
+          ERN_TW(if (etr) ec0 = clock64();)
+          const CompactResult cr = warp_compact_segment(seg, cnt, thr, thr_ord_q, full, sink.k, keep_max);
+          cnt = cr.cnt;
+          thr = cr.thr;
+          ERN_TW(if (etr) { e_comp += clock64() - ec0; ++n_comp; })
+        }
       }
       // publish how many candidates this unit holds for the query
       if (live) *cnt_q = cnt;
     }
+#ifdef ERN_SIM_TRACE_WAITS
+    if (etr) {
+      unsigned long long* o = p.trace + static_cast<size_t>(unit) * 8;
+      o[5] += static_cast<unsigned long long>(clock64() - e_begin);
+      o[6] += static_cast<unsigned long long>(e_wait);
+      o[7] += static_cast<unsigned long long>(e_comp);
+      o[4] += static_cast<unsigned long long>(n_comp) << 40;      // (shares the slot with the query-tile wait cycles)
+      unsigned long long* o2 = p.trace + static_cast<size_t>(148 + unit) * 8;   // second block: tile-time tail of this warp
+      o2[0] += n_t4; o2[1] += n_t8; o2[2] += n_t16;
+      if (static_cast<unsigned long long>(e_tmax) > o2[3]) o2[3] = e_tmax;
+    }
+#endif
   }
 
   // ================================ teardown ================================
@@ -404,6 +493,12 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& si
   p.gallery_rows = gallery_rows;
   p.row_bytes = dim * 2;
   p.prefetch_tiles = p.gallery_base ? pf : 0;
+  // ERN_TRACE_PTR: device address of a zeroed u64[8 * units] buffer owned by the profiling tool (tools/trace_sim.py)
+  static unsigned long long* const trace = [] {
+    const char* e = getenv("ERN_TRACE_PTR");
+    return e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }();
+  p.trace = trace;
   p.num_kblocks = dim / kBlockK;
   p.n_qtiles = cdiv(sink.nq, pair ? 2 * kBlockQ : kBlockQ);
   p.tiles_total = cdiv(sink.row_end - sink.row_begin, tile_g);

@@ -8,6 +8,8 @@ branch is refused (no backward on the accelerated path).
 """
 from __future__ import annotations
 
+import warnings
+
 import torch
 from torch import nn
 
@@ -27,6 +29,8 @@ class _ClipPassThrough(nn.Module):
 
     def forward(self, x, mode="global", visual_emb=None):
         clip = object.__getattribute__(self, "_clip")
+        if hasattr(clip, "eval"):
+            clip.eval()                                   # models/clip_model.py:11,24
         with torch.no_grad():
             if self.kind == "image":
                 return clip.encode_image(x)
@@ -52,10 +56,34 @@ class ERN(nn.Module):
         self.Combiner_module.set_mode(mode)
         return self
 
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """Same keys as the reference's: when the wrapped CLIP model is an ``nn.Module`` its weights appear under
+        ``image_clip.clip_model.*`` and ``text_clip.clip_model.*`` (models/clip_model.py:8,21 register it twice)."""
+        sd = super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
+        clip = object.__getattribute__(self.image_clip, "_clip")
+        if isinstance(clip, nn.Module):
+            for tower in ("image_clip", "text_clip"):
+                clip.state_dict(destination=sd, prefix=f"{prefix}{tower}.clip_model.", keep_vars=keep_vars)
+        return sd
+
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         """Reference checkpoints (``torch.save(model.module.state_dict())``, run/train/train_fiq.py:174-175) may
         carry CLIP keys under ``image_clip.`` / ``text_clip.`` and HF ``position_ids`` buffers, and lack
         ``DVR.transformer_layer.cls_token`` when they were built on CUDA: all handled here."""
+        clip = object.__getattribute__(self.image_clip, "_clip")
+        clip_sd = {k.split("clip_model.", 1)[1]: v for k, v in state_dict.items()
+                   if k.startswith(("image_clip.clip_model.", "text_clip.clip_model."))}
+        if clip_sd:
+            # the reference registers clip_model as a submodule (models/clip_model.py:8,19), so its checkpoints carry
+            # the backbone and its load_state_dict restores it: forward those keys into the caller's CLIP model
+            if isinstance(clip, nn.Module):
+                missing, unexpected = clip.load_state_dict(clip_sd, strict=False)
+                if unexpected or len(missing) == len(clip.state_dict()):
+                    warnings.warn(f"checkpoint CLIP weights did not match the wrapped CLIP model "
+                                  f"({len(unexpected)} unexpected, {len(missing)} missing keys)")
+            else:
+                warnings.warn("the checkpoint carries CLIP backbone weights (image_clip.* / text_clip.*) but the wrapped "
+                              "clip_model is not an nn.Module: they were NOT loaded; make sure --clip-path matches")
         sd = {k: v for k, v in state_dict.items()
               if not k.startswith(("image_clip.", "text_clip.")) and not k.endswith("position_ids")}
         if "DVR.transformer_layer.cls_token" not in sd:

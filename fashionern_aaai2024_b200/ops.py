@@ -12,7 +12,7 @@ import torch
 
 from . import _lib as L
 from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, QUERY_BATCH, RANK_REFERENCE,
-                   RANK_SIMILARITY, SORT_CAP, ErnError)
+                   RANK_SIMILARITY, SEG_CAP, SORT_CAP, ErnError)
 
 __all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "gather_scores",
            "cirr_subset_from_scores", "bbc_loss_forward", "bbc_loss_backward", "launch_counter"]
@@ -86,7 +86,7 @@ def _sim_launches(nq: int, n_rows: int, k: int, growth: int, mode: int, device) 
         bq = min(QUERY_BATCH, nq - q0)
         cap = None
         if mode == MODE_FP32:
-            cap = (sms // 2 if bq > 128 else sms) * (128 if k <= 64 else 256)
+            cap = (sms // 2 if bq > 128 else sms) * SEG_CAP
         total += 1 + 2 * _phase_count(n_rows, k, growth, cap)
     return total
 

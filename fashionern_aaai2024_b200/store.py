@@ -136,19 +136,25 @@ class FeatureStore:
         pin = torch.cuda.is_available() and torch.device(device).type == "cuda"
         stages = [torch.empty((chunk_rows,) + tuple(arr.shape[1:]), dtype=torch.int16, pin_memory=pin) for _ in range(2)]
         events = [None, None]
+        # the copies run on the DESTINATION device's current stream: record / synchronize on that stream, not on the
+        # stream of whatever device happens to be current in this process
+        stream = torch.cuda.current_stream(out.device) if pin else None
         for n, s in enumerate(range(begin, end, chunk_rows)):
             e = min(s + chunk_rows, end)
             st = stages[n & 1]
             if events[n & 1] is not None:
                 events[n & 1].synchronize()                      # staging buffer free again
             st[:e - s].numpy().view(np.uint16)[...] = arr[s:e]
-            out[s - begin:e - begin].view(torch.int16).copy_(st[:e - s], non_blocking=True)
             if pin:
-                ev = torch.cuda.Event()
-                ev.record()
+                with torch.cuda.device(out.device), torch.cuda.stream(stream):
+                    out[s - begin:e - begin].view(torch.int16).copy_(st[:e - s], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
                 events[n & 1] = ev
+            else:
+                out[s - begin:e - begin].view(torch.int16).copy_(st[:e - s])
         if pin:
-            torch.cuda.current_stream().synchronize()
+            stream.synchronize()
         return out
 
     def load_shard(self, rank: int = 0, world_size: int = 1, device="cuda", chunk_rows: int = 1 << 16

@@ -54,11 +54,11 @@ extern "C" {
 #define ERN_RANK_REFERENCE 1  /* -(1 - s) rounded in fp32: the reference's `1 - pred @ index.T`    */
                               /* (run/test/test_fiq.py:49) with its rounding-induced ties          */
 
-/* max k of the streaming top-k; slots of one candidate segment (one per query and persistent scoring unit; 128 when
- * k <= 64); max candidates the selection/merge kernel stages in shared memory (more are handled from L2); queries that
+/* max k of the streaming top-k; slots of one candidate segment (one per query and persistent scoring unit: room for
+ * the survivors of a pruning pass plus every score of one 256-row gallery tile); max candidates the selection/merge kernel stages in shared memory (more are handled from L2); queries that
  * go through the launch schedule together (larger batches are processed ERN_QUERY_BATCH at a time) */
 #define ERN_MAX_K 128
-#define ERN_SEG_CAP 256
+#define ERN_SEG_CAP 512
 #define ERN_SORT_CAP 2048
 #define ERN_QUERY_BATCH 4096
 /* gallery rows scored densely (every score kept) before thresholds exist; also the slots of a query's prefix list */

@@ -112,3 +112,53 @@ class SeededClip:
         if mode == "seq":
             return self.text_seq[idx]
         return self.text_global[idx], None
+
+
+# ---------------------------------------------------------------------------------------------------
+# Tight bf16 checks: the oracle on the SAME bf16-rounded operands, exact up to near-ties
+# ---------------------------------------------------------------------------------------------------
+TIE_TOL = 2.2e-6   # fp32 accumulation order + the rounding of 1 - s: ranks may differ only inside such gaps
+
+
+def rounded(t):
+    """What the bf16 tail actually scores: the fp32 features rounded to bf16 (metrics._operands), upcast again."""
+    return t.detach().float().cpu().bfloat16().float()
+
+
+def unique_oracle_with_ties(pred_r, gal_r, names, tgt_names, ks, anyhit=False, tol=TIE_TOL):
+    """Oracle Recall tuple on the given operands + per K the number of queries whose ranks K-1 / K are closer than
+    ``tol`` (only those may legitimately land on the other side of the K boundary)."""
+    from oracle import ern_oracle as orc
+    # == orc.fiq_metrics / orc.f200k_metrics (one ranking pass serves both the tuple and the tie census)
+    if not anyhit:
+        orc.check_unique_targets(names, tgt_names)
+    gcls, tcls = orc.factorize(names, tgt_names)
+    ids, d = orc.rank_topk(pred_r, gal_r, max(ks) + 1)
+    want = orc.recall_at(orc.first_hit_rank(ids[:, :max(ks)], gcls, tcls), ks)
+    near = [int(((d[:, k] - d[:, k - 1]).abs() < tol).sum()) if k < d.shape[1] else 0 for k in ks]
+    return want, near
+
+
+def cirr_oracle_with_ties(pred_r, gal_r, names, ref_names, tgt_names, members, tol=TIE_TOL):
+    """Oracle CIRR 7-tuple (G@1,G@2,G@3,R@1,R@5,R@10,R@50) on the given operands + per entry the number of queries
+    that sit inside a near-tie at that decision (K boundary of the reference-free ranking; target vs another group
+    member for the subset ranks)."""
+    from oracle import ern_oracle as orc
+    want = orc.cirr_metrics(pred_r, gal_r, names, ref_names, tgt_names, members)
+    idx = {nm: i for i, nm in enumerate(names)}
+    ref_idx = torch.tensor([idx[r] for r in ref_names])
+    _, d = orc.rank_topk(pred_r, gal_r, 51, exclude_index=ref_idx)
+    near_r = [int(((d[:, k] - d[:, k - 1]).abs() < tol).sum()) for k in (1, 5, 10, 50)]
+    dist = orc.distances(pred_r, gal_r)
+    near_g = 0
+    for i, (r, t, mem) in enumerate(zip(ref_names, tgt_names, members)):
+        dt = dist[i, idx[t]]
+        others = [idx[m] for m in mem if m in idx and m != r and m != t]
+        if others and float((dist[i, others] - dt).abs().min()) < tol:
+            near_g += 1
+    return want, [near_g] * 3 + near_r
+
+
+def assert_tuple_within_ties(got, want, near, q):
+    for j, (a, b, nr) in enumerate(zip(got, want, near)):
+        assert abs(a - b) <= 100.0 * nr / q + 1e-9, (j, a, b, nr)

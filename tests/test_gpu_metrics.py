@@ -47,18 +47,31 @@ def test_fp32_mode_reproduces_reference_tuple(cuda_device, name):
 
 
 @pytest.mark.parametrize("name", ["fiq640", "val512", "shoes640", "f200k640", "cirr640"])
-def test_bf16_mode_matches_up_to_near_ties(cuda_device, name):
+def test_bf16_mode_is_exact_on_its_own_operands(cuda_device, name):
+    """bf16 product path, tight: the drop-in function's tuple must EQUAL the oracle's tuple computed from the same
+    bf16-rounded operands (the query features and the fused gallery the function itself scores), except for queries
+    sitting inside a 2.2e-6 near-tie at a decision boundary (run/test/test_cirr.py:55-78 and twins).  The heads'
+    bf16 error is bounded separately (tests/test_gpu_combiner.py); a loose check against the fp32 reference tuple
+    guards against gross drift."""
+    from helpers import assert_tuple_within_ties, cirr_oracle_with_ties, rounded, unique_oracle_with_ties
     z, meta, ds, feats, local, names, model = build(name, cuda_device, "bf16")
-    out = FN[meta["kind"]](ds, FakeClip(meta["dim"]), feats, local, names, model, cuda_device, meta["dim"], 32, 0,
-                           "RN50x4", precision="bf16")
-    ref = z["recall"].tolist()
-    q = meta["q"]
-    # bf16 operand rounding perturbs each score by <= ~1e-3: a query may cross a K boundary only
-    # if its target sits within that distance of the boundary in the reference ranking
+    kind, q, dim = meta["kind"], meta["q"], meta["dim"]
+    out = FN[kind](ds, FakeClip(dim), feats, local, names, model, cuda_device, dim, 32, 0, "RN50x4", precision="bf16")
+    pred_r = rounded(torch.from_numpy(z["pred"]))                      # StandInERN serves the recorded predictions
+    gal_r = rounded(metrics.prepare_gallery(feats, local, model, cuda_device))
+    if kind == "cirr":
+        want, near = cirr_oracle_with_ties(pred_r, gal_r, names, ds.ref, ds.tgt, ds.members)
+    else:
+        want, near = unique_oracle_with_ties(pred_r, gal_r, names, ds.tgt, KS[kind], anyhit=(kind == "200k"))
+    assert_tuple_within_ties(out, want, near, q)
+    # vs the fp32 reference tuple: bf16 operand rounding (<= ~1e-3 per score, SURVEY.md P3) may move a query across a
+    # K boundary only if its target sits that close to the boundary in the reference ranking
     d = z["ref_dist"]
-    for got, want, k in zip(out, ref, KS[meta["kind"]]):
-        near = int(np.sum(np.abs(d[:, min(k, d.shape[1] - 1)] - d[:, k - 1]) < 4e-3)) if meta["kind"] != "cirr" else q
-        assert abs(got - want) <= 100.0 * near / q + 1e-9, (k, got, want, near)
+    for j, (got, ref, k) in enumerate(zip(out, z["recall"].tolist(), KS[kind])):
+        if kind == "cirr" and j < 3:
+            continue                                                    # subset ranks: covered exactly above
+        nr = int(np.sum(np.abs(d[:, min(k, d.shape[1] - 1)] - d[:, k - 1]) < 4e-3))
+        assert abs(got - ref) <= 100.0 * nr / q + 1e-9, (k, got, ref, nr)
 
 
 def test_8_argument_form_and_print(cuda_device, capsys):

@@ -4,10 +4,13 @@ import json
 import sys
 import os
 
+import time
+
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fashionern_aaai2024_b200 import ops  # noqa: E402
+from bench import ClockSampler, make_gallery  # noqa: E402
 
 
 def main():
@@ -18,19 +21,20 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--growth", type=int, default=8)
+    ap.add_argument("--order", default="random", choices=["random", "clustered"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     gen = torch.Generator(device=dev).manual_seed(1)
-    gal = torch.empty(args.n, args.dim, dtype=torch.bfloat16, device=dev)
-    step = 1 << 20
-    for s in range(0, args.n, step):
-        x = torch.randn(min(step, args.n - s), args.dim, generator=gen, device=dev)
-        gal[s:s + step] = torch.nn.functional.normalize(x, dim=-1).bfloat16()
+    gal = make_gallery(args.n, args.dim, dev, 1, args.order)
     pred = torch.nn.functional.normalize(torch.randn(args.q, args.dim, generator=gen, device=dev), dim=-1).bfloat16()
     for _ in range(2):
         out = ops.sim_topk(pred, gal, args.k, growth=args.growth, check_overflow=False)
     torch.cuda.synchronize()
     st = out[3].cpu().tolist()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
+    t0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.iters):
@@ -38,9 +42,11 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
+    clocks = sampler.stop(t0, time.time())
     flops = 2.0 * args.q * args.n * args.dim
     print(json.dumps({"q": args.q, "n": args.n, "dim": args.dim, "k": args.k, "ms": ms,
-                      "tflops": flops / ms / 1e9, "qps": args.q / ms * 1e3, "status": st,
+                      "tflops": flops / ms / 1e9, "qps": args.q / ms * 1e3, "status": st, "order": args.order,
+                      "sm_mhz": clocks.get("sm_mhz"), "power_w": clocks.get("power_w_max"), "lib": os.path.basename(os.environ.get("ERN_B200_LIB", "head")),
                       "single": os.environ.get("ERN_FORCE_SINGLE_CTA", "0")}))
 
 
