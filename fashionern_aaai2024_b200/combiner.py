@@ -111,8 +111,10 @@ class CombinerSimple(nn.Module):
             L.check(lib.ern_combiner_forward(C.byref(w), self.dim, mode, img.data_ptr(), txt.data_ptr(), rows,
                                              out.data_ptr(), L.ptr(out_b), self.dim, None, ws.data_ptr(), wsb,
                                              L.stream_ptr(dev)))
-            # bf16: 2 casts, 2 projection GEMMs, gate GEMM, finaliser;  fp32: 2 projections, hidden+gate, finaliser
-            launch_counter.add(0 if not rows else (6 if mode == MODE_BF16 else 4))
+            # bf16: 2 casts, 2 projection GEMMs, gate GEMM, finaliser (<= 64 rows: ONE cooperative weight-streaming launch);
+            # fp32: 2 projections, hidden+gate, finaliser
+            small = mode == MODE_BF16 and rows <= 64 and self.dim % 64 == 0
+            launch_counter.add(0 if not rows else (1 if small else 6 if mode == MODE_BF16 else 4))
         if out_dtype != torch.float32:
             out = out.to(out_dtype)
         return (out, out_b) if want_bf16 else out

@@ -21,7 +21,9 @@ static size_t al(size_t x) { return (x + 255) & ~size_t(255); }
 
 size_t workspace_bytes_bf16(int64_t rows, int dim) {
   const size_t r = rows, d = dim;
-  return al(r * d * 2) * 2 + al(r * 8 * d * 2) + al(r * (8 * d / kGemmBlockN) * 4) + 512;
+  // (the small-batch path keeps one gate partial per CTA, up to 8D / 32 of them, instead of one per 256-column tile)
+  const size_t n_part = rows <= 64 ? 8 * d / 32 : 8 * d / kGemmBlockN;
+  return al(r * d * 2) * 2 + al(r * 8 * d * 2) + al(r * n_part * 4) + 512;
 }
 
 int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, const float* text, int64_t rows,
@@ -37,6 +39,12 @@ int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, con
   float* partial = reinterpret_cast<float*>(ws + 2 * al(r * d * 2) + al(r * 8 * d * 2));
   const int n_tiles = hid / kGemmBlockN;
   PackedView pv = view_packed(w->packed_bf16, dim);
+  if (small::supported(rows, dim, sm_count)) {
+    // weight-bandwidth-bound regime (the reference's 32-row query batches): one cooperative weight-streaming launch.
+    // NOTE: its grid-barrier counters live in the packed-weights buffer, so forward calls that share one packed
+    // buffer must be ordered on one stream (they always are for a module called from one Python thread).
+    return small::forward(pv, pv.sync, dim, image, text, rows, raw, partial, out, out_bf16, ldb, gate, sm_count, st);
+  }
 
   int rc = launch_cast_bf16(image, img_b, rows * d, st);
   if (rc) return rc;

@@ -40,6 +40,7 @@ namespace combiner {
 struct PackedView {
   const __nv_bfloat16 *wt, *wi, *w1;
   const float *bt, *bi, *b1, *w2, *b2;
+  unsigned* sync;   // [4] counters of the small-batch kernel, zero between calls
 };
 PackedView view_packed(const void* packed, int dim);
 int launch_finalize(const float* image, const float* text, int64_t rows, int dim, const float* partial, int n_tiles,
@@ -54,6 +55,13 @@ size_t workspace_bytes_bf16(int64_t rows, int dim);
 int forward_bf16(const ern_combiner_weights* w, int dim, const float* image, const float* text, int64_t rows,
                  float* out, void* out_bf16, int64_t ldb, float* gate, void* workspace, int sm_count,
                  cudaStream_t st);
+namespace small {   // <= 64 rows: weight-streaming kernels (ern_combiner_small.cu)
+bool supported(int64_t rows, int dim, int sm_count);
+int n_partials(int dim, int sm_count);
+int forward(const PackedView& pv, unsigned* sync, int dim, const float* image, const float* text, int64_t rows,
+            __nv_bfloat16* raw, float* partial, float* out, void* out_bf16, int64_t ldb, float* gate, int sm_count,
+            cudaStream_t st);
+}
 }
 
 namespace dvr {

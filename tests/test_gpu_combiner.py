@@ -52,6 +52,27 @@ def test_ragged_batches_against_oracle(cuda_device, rows, mode):
     assert rows < 100 or float(gate.max() - gate.min()) > 0.2                    # the synthetic gate is informative
 
 
+@pytest.mark.parametrize("dim", [640, 512, 768])
+@pytest.mark.parametrize("rows", [1, 15, 16, 17, 31, 32, 33, 48, 64, 65])
+def test_small_batches_weight_streaming_path(cuda_device, dim, rows):
+    """<= 64 rows take the weight-streaming kernels (ern_combiner_small.cu; the reference's query side runs 32-row
+    batches, run/test/test_fiq.py:132); 65 rows is the first size back on the tcgen05 GEMMs.  Same tolerance, both
+    outputs, and the result must not depend on which path a row went through."""
+    sd = syn.combiner_state(91, dim)
+    m = make(dim, 91, "bf16", cuda_device)
+    img, txt = syn.features(92, rows, dim), syn.features(93, rows, dim, unit=True)
+    ref = orc.combiner_forward(sd, img, txt)
+    with torch.no_grad():
+        out, out_b = m(img.to(cuda_device), txt.to(cuda_device), want_bf16=True)
+        big = m(torch.cat([img, syn.features(94, 200, dim)]).to(cuda_device),
+                torch.cat([txt, syn.features(95, 200, dim, unit=True)]).to(cuda_device))[:rows]
+    assert float((out.cpu() - ref).norm(dim=-1).max()) <= TOL_BF16
+    assert float((out_b.float().cpu() - out.cpu()).abs().max()) <= 2 ** -8
+    # small path vs tcgen05 path on the same rows: both are bf16 operands with fp32 accumulation
+    assert float((out - big).norm(dim=-1).max()) <= 2e-3
+    assert torch.isfinite(out).all()
+
+
 def test_dvr_call_site_inputs(cuda_device):
     # the three query-side call sites (models/fusion_model.py:52-54) with the inputs the reference recorded
     z, meta = load_golden("fiq640")
