@@ -54,6 +54,7 @@ struct SimWorkspace {
   int32_t* prev_counts;
   int32_t* seg_counts;
   uint32_t* thr_ord;
+  int32_t* sel_flags;
   size_t bytes;
 };
 // One query batch (<= ERN_QUERY_BATCH queries) at a time goes through the launch schedule; the workspace holds the
@@ -71,6 +72,8 @@ static SimWorkspace carve_sim(void* base, int64_t batch, int n_seg, int seg_cap)
   w.seg_counts = reinterpret_cast<int32_t*>(p + off);
   off += align256(static_cast<size_t>(batch) * n_seg * 4);
   w.thr_ord = reinterpret_cast<uint32_t*>(p + off);
+  off += align256(static_cast<size_t>(batch) * 4);
+  w.sel_flags = reinterpret_cast<int32_t*>(p + off);
   off += align256(static_cast<size_t>(batch) * 4);
   w.bytes = off;
   return w;
@@ -355,6 +358,7 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
   for (int64_t q0 = 0; q0 < nq; q0 += ERN_QUERY_BATCH) {
     const int64_t bq = nq - q0 < ERN_QUERY_BATCH ? nq - q0 : ERN_QUERY_BATCH;
     const int n_seg = simtc::units_for(bq, force_single(), di.sm_count);
+    ERN_REQUIRE(n_seg <= 256, "internal: %d scoring units exceed the selection kernel's segment table", n_seg);
     SimWorkspace ws = carve_sim(workspace_dev, bq, n_seg, seg_cap);
     const uint8_t* qbase = static_cast<const uint8_t*>(queries_dev) + static_cast<size_t>(q0) * ldq * esize;
     if (mode == ERN_MODE_BF16) {
@@ -389,6 +393,7 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
     sp.single_segment = mode == ERN_MODE_FP32 ? 1 : 0;
     sp.k = k;
     sp.thr_ord = ws.thr_ord;
+    sp.sel_flags = mode == ERN_MODE_BF16 ? ws.sel_flags : nullptr;
     sp.status = status_dev;
     sp.world = world;
     sp.rank = rank;

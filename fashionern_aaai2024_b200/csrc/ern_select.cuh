@@ -33,5 +33,7 @@ struct SelectParams {
   int64_t nq_total;          // queries of the whole call (row stride of the peer buffers)
   int64_t q_first;           // index of this batch's first query within the call (peer buffer row offset)
   int32_t* status;
+  // [nq] (nullable) written by select_topk_warp_kernel: 0 = done by it, 1 = left to select_topk_kernel
+  int32_t* sel_flags;
 };
 }  // namespace ern

@@ -33,16 +33,22 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* a, int pow2, int tid
 }
 
 constexpr int kSmallSort = 256;  // candidates that are sorted directly / survivors of the radix select
+constexpr int kMaxSegments = 256;  // >= persistent scoring units (148 CTAs on a B200)
 
-__global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const SelectParams p) {
+__global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const SelectParams p, const int64_t nq) {
   __shared__ uint64_t keys[ERN_SORT_CAP];
   __shared__ uint64_t top[kSmallSort];
   __shared__ int hist[256];
   __shared__ int n_shared, m_shared, remaining_sh, ge_sh;
   __shared__ uint64_t prefix_sh;
-  const int64_t q = blockIdx.x;
+  __shared__ int seg_off[kMaxSegments + 1];     // exclusive prefix sums of the segment counts of this query
   const int tid = threadIdx.x;
   const int k = p.k;
+  // one block per query -- or, behind select_topk_warp_kernel, a small grid that walks the flags and only works on
+  // the queries that kernel left over
+  for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+  if (p.sel_flags && p.sel_flags[q] == 0) continue;  // select_topk_warp_kernel has already done this query
+  __syncthreads();                                   // (shared state of the previous query is no longer in use)
   // (read before the kernel's last step overwrites it; dense launches and merges have no bound yet)
   const uint32_t thr_floor = (p.n_lists == 0 && p.dense_count == 0 && p.thr_ord) ? p.thr_ord[q] : 0u;
   if (tid == 0) {
@@ -51,6 +57,26 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
     remaining_sh = k;
     prefix_sh = 0;
     ge_sh = 0;
+  }
+  if (p.n_lists == 0 && p.dense_count == 0 && !p.single_segment) {
+    // segment counts -> exclusive prefix sums (one coalesced read, one warp scan per 32 segments)
+    const int32_t* sc = p.seg_counts + q * p.n_seg;
+    if (tid < 32) {
+      int carry = 0;
+      for (int base = 0; base < p.n_seg; base += 32) {
+        const int u = base + tid;
+        const int c = u < p.n_seg ? min(sc[u], p.seg_cap) : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += v;
+        }
+        if (u < p.n_seg) seg_off[u] = carry + incl - c;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (tid == 0) seg_off[p.n_seg] = carry;
+    }
   }
   __syncthreads();
 
@@ -82,14 +108,17 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
         if (key >= floor_key) f(key);
       }
     } else {
-      // one warp per segment: coalesced reads of exactly the published entries
-      for (int u = tid >> 5; u < p.n_seg; u += kSelectThreads / 32) {
-        const int cnt = min(sc[u], p.seg_cap);
-        const uint64_t* seg = segs + static_cast<int64_t>(u) * p.seg_cap;
-        for (int i = tid & 31; i < cnt; i += 32) {
-          const uint64_t key = seg[i];
-          if (key >= floor_key) f(key);
+      // flat walk over the published entries of all segments: every thread's loads are independent of each other (a
+      // warp-per-segment walk chained a count load and a key load per segment: ~10 dependent L2 round trips per query)
+      const int total = seg_off[p.n_seg];
+      for (int i = tid; i < total; i += kSelectThreads) {
+        int lo = 0, hi = p.n_seg;                      // segment u with seg_off[u] <= i < seg_off[u + 1]
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (seg_off[mid] <= i) lo = mid; else hi = mid;
         }
+        const uint64_t key = segs[static_cast<int64_t>(lo) * p.seg_cap + (i - seg_off[lo])];
+        if (key >= floor_key) f(key);
       }
     }
   };
@@ -215,11 +244,218 @@ __global__ void __launch_bounds__(kSelectThreads) select_topk_kernel(const Selec
     // fewer than k real candidates so far: no lower bound yet
     if (p.thr_ord) p.thr_ord[q] = kth ? static_cast<uint32_t>(kth >> 32) : f32_to_ordered(-INFINITY);
   }
+  }  // query loop
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// The same selection with ONE WARP per query and the candidates in registers (<= 32 per lane): the usual case between
+// two scoring launches is a few hundred candidates per query, for which a 256-thread block spends its time in
+// barriers, same-bin shared-memory atomics and dependent global loads (76 us per launch for 4096 queries; this one:
+// a few us).  Exact top-k of the unique 64-bit keys: MSB-first one-bit radix search that skips the bits all values
+// share and stops as soon as exactly k keys remain, then a 128-key warp bitonic sort.  Queries with more than
+// kWarpSelMax candidates (ordered galleries) are flagged and left to select_topk_kernel, which runs right after.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kWarpSelMax = 1024;
+constexpr int kWarpsPerBlock = 8;
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) select_topk_warp_kernel(const SelectParams p, int64_t nq) {
+  __shared__ int seg_off_s[kWarpsPerBlock][kMaxSegments + 1];
+  __shared__ uint64_t sortbuf_s[kWarpsPerBlock][128];
+  const unsigned kFull = 0xffffffffu;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * kWarpsPerBlock + w;
+  if (q >= nq) return;
+  const int k = p.k;
+  int* seg_off = seg_off_s[w];
+  uint64_t* sortbuf = sortbuf_s[w];
+  const bool dense = p.dense_count > 0;
+  const uint32_t thr_floor = (!dense && p.thr_ord) ? p.thr_ord[q] : 0u;
+  const uint64_t floor_key = static_cast<uint64_t>(thr_floor) << 32;
+  const int np = dense ? p.dense_count : p.prev_counts[q];
+  int total = 0;
+  if (!dense) {
+    const int32_t* sc = p.seg_counts + q * p.n_seg;
+    int carry = 0;
+    for (int base = 0; base < p.n_seg; base += 32) {
+      const int u = base + lane;
+      const int c = u < p.n_seg ? min(sc[u], p.seg_cap) : 0;
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (u < p.n_seg) seg_off[u] = carry + incl - c;
+      carry += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) seg_off[p.n_seg] = carry;
+    total = carry;
+    __syncwarp();
+  }
+  if (np + total > kWarpSelMax) {
+    if (lane == 0) p.sel_flags[q] = 1;
+    return;
+  }
+  if (lane == 0) p.sel_flags[q] = 0;
+
+  // ---- candidates -> registers (flat index lane + 32 j over [prefix | segment 0 | segment 1 | ...]) ----------------
+  const uint64_t* pre = p.prefix + q * ERN_DENSE_ROWS;
+  const uint64_t* segs = p.segs + q * static_cast<int64_t>(p.n_seg) * p.seg_cap;
+  // pass 1 only issues the loads (the flat index grows by 32 per step, so the segment cursor only moves forward: no
+  // search); pass 2 consumes them -- all of a lane's loads are in flight together
+  uint64_t key[32];
+  int seg_u = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int i = lane + 32 * j;
+    key[j] = 0ull;
+    if (i < np) {
+      key[j] = pre[i];
+    } else if (i < np + total) {
+      const int f = i - np;
+#pragma unroll 1
+      while (seg_off[seg_u + 1] <= f) ++seg_u;     // (segment with seg_off[u] <= f < seg_off[u + 1]; empty ones are skipped)
+      key[j] = segs[static_cast<int64_t>(seg_u) * p.seg_cap + (f - seg_off[seg_u])];
+    }
+  }
+  uint32_t hi[32], lo[32];
+  int n_real = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const uint64_t kj = key[j] < floor_key ? 0ull : key[j];   // below the query's published lower bound: cannot be among the k best
+    hi[j] = static_cast<uint32_t>(kj >> 32);
+    lo[j] = static_cast<uint32_t>(kj);
+    n_real += kj != 0ull;
+  }
+  n_real = __reduce_add_sync(kFull, n_real);
+
+  // ---- which keys are among the k largest?  keep := hi > pre_hi || (hi == pre_hi && lo >= pre_lo) ------------------
+  uint32_t pre_hi = 0u, pre_lo = 0u;               // n_real <= k: every real key stays (the key != 0 test below)
+  if (n_real > k) {
+    uint32_t vmax = 0u, vmin = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if ((hi[j] | lo[j]) != 0u) {
+        vmax = max(vmax, hi[j]);
+        vmin = min(vmin, hi[j]);
+      }
+    }
+    vmax = __reduce_max_sync(kFull, vmax);
+    vmin = __reduce_min_sync(kFull, vmin);
+    const int top = 31 - __clz(vmax ^ vmin);       // bits above `top` are shared by every value; -1: all values equal
+    pre_hi = top >= 31 ? 0u : (vmax >> (top + 1)) << (top + 1);
+    int rem = k, bucket = n_real;                  // the k-th largest key is the rem-th largest of the current bucket
+#pragma unroll 1
+    for (int b = top; b >= 0 && bucket != rem; --b) {
+      const uint32_t cand = (pre_hi | (1u << b)) >> b;
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) c += ((hi[j] >> b) == cand) ? 1 : 0;
+      c = __reduce_add_sync(kFull, c);
+      if (c >= rem) { pre_hi |= 1u << b; bucket = c; } else { rem -= c; bucket -= c; }
+    }
+    if (bucket != rem) {
+      // every value bit is decided and more keys than needed carry exactly the k-th value: the id half decides
+      // (ids are unique; lower id = larger lo wins)
+#pragma unroll 1
+      for (int b = 31; b >= 0 && bucket != rem; --b) {
+        const uint32_t cand = (pre_lo | (1u << b)) >> b;
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) c += (hi[j] == pre_hi && (lo[j] >> b) == cand) ? 1 : 0;
+        c = __reduce_add_sync(kFull, c);
+        if (c >= rem) { pre_lo |= 1u << b; bucket = c; } else { rem -= c; bucket -= c; }
+      }
+    }
+  }
+  const int m = n_real < k ? n_real : k;
+  // ---- survivors -> 128-slot buffer ----------------------------------------------------------------------------------
+  for (int i = lane; i < 128; i += 32) sortbuf[i] = 0ull;
+  __syncwarp();
+  int base = 0;
+  uint32_t min_hi = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const bool keep = (hi[j] | lo[j]) != 0u && (hi[j] > pre_hi || (hi[j] == pre_hi && lo[j] >= pre_lo));
+    const unsigned mk = __ballot_sync(kFull, keep);
+    if (keep) {
+      sortbuf[base + __popc(mk & ((1u << lane) - 1u))] = (static_cast<uint64_t>(hi[j]) << 32) | lo[j];
+      min_hi = min(min_hi, hi[j]);
+    }
+    base += __popc(mk);
+  }
+  __syncwarp();
+  if (base != m && lane == 0 && p.status) atomicAdd(&p.status[0], 1);   // cannot happen (keys are unique)
+  min_hi = __reduce_min_sync(kFull, min_hi);        // ranking value of the k-th best when m == k
+  uint64_t e[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) e[r] = sortbuf[lane + 32 * r];
+  // Only a launch that emits results needs them in order; between two scoring launches the prefix is a SET (both
+  // selection kernels read it as one), so the 128-key bitonic sort -- a third of this kernel's instructions -- is skipped.
+  const bool emit = p.out_keys || p.peer_keys || p.out_scores || p.out_ids;
+  if (emit) {
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int idx = lane + 32 * r;
+          const bool am_lower = (idx & stride) == 0;
+          const bool desc = ((idx & ~stride) & size) == 0;
+          uint64_t other;
+          if (stride >= 32) {
+            other = e[r ^ (stride >> 5)];
+          } else {
+            other = __shfl_xor_sync(kFull, e[r], stride);
+          }
+          const uint64_t mx = e[r] > other ? e[r] : other, mn = e[r] > other ? other : e[r];
+          // (in-register partners are both updated in this pass: compute from the values before the pass)
+          sortbuf[idx] = (desc == am_lower) ? mx : mn;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) e[r] = sortbuf[lane + 32 * r];
+        __syncwarp();
+      }
+    }
+  }
+  // ---- outputs (same contract as select_topk_kernel; the prefix is only sorted on emitting launches) ---------------
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int j = lane + 32 * r;
+    if (j < k) {
+      const uint64_t key = e[r];
+      if (p.prefix) p.prefix[q * ERN_DENSE_ROWS + j] = key;
+      if (p.out_keys) p.out_keys[q * k + j] = key;
+      if (p.peer_keys) {
+        const int64_t slot = (static_cast<int64_t>(p.rank) * p.nq_total + p.q_first + q) * k + j;
+        for (int s2 = 0; s2 < p.world; ++s2) p.peer_keys[s2][slot] = key;
+      }
+      if (p.out_scores) p.out_scores[q * k + j] = key ? key_value(key) : -INFINITY;
+      if (p.out_ids) p.out_ids[q * k + j] = key ? key_id(key) : -1;
+    }
+  }
+  if (!dense)
+    for (int u = lane; u < p.n_seg; u += 32) p.seg_counts[q * p.n_seg + u] = 0;
+  if (lane == 0) {
+    if (p.prev_counts) p.prev_counts[q] = m;
+    if (p.thr_ord) p.thr_ord[q] = (m == k) ? min_hi : f32_to_ordered(-INFINITY);
+  }
 }
 
 int launch_select(const SelectParams& p, int64_t nq, cudaStream_t st) {
   if (nq <= 0) return ERN_OK;
-  select_topk_kernel<<<static_cast<unsigned>(nq), kSelectThreads, 0, st>>>(p);
+  // a query's own candidates (tensor-core path): warp-per-query kernel first; it flags the queries it leaves to the
+  // block kernel (more than kWarpSelMax candidates), which returns immediately for all the others
+  unsigned grid = static_cast<unsigned>(nq);
+  if (p.sel_flags && p.n_lists == 0 && !p.single_segment) {
+    select_topk_warp_kernel<<<cdiv(nq, kWarpsPerBlock), 32 * kWarpsPerBlock, 0, st>>>(p, nq);
+    ERN_CUDA(cudaGetLastError());
+    if (grid > 296u) grid = 296u;                   // leftovers are rare: two blocks per SM walk the flags
+  }
+  select_topk_kernel<<<grid, kSelectThreads, 0, st>>>(p, nq);
   ERN_CUDA(cudaGetLastError());
   return ERN_OK;
 }
