@@ -81,6 +81,16 @@ static SimWorkspace carve_sim(void* base, int64_t batch, int n_seg, int seg_cap)
 // slots per segment: the survivors of a pruning pass (<= 256) plus every score of one 256-row gallery tile
 static int seg_cap_for(int k) { (void)k; return ERN_SEG_CAP; }
 
+// most gallery rows of one tensor-core scoring launch (ERN_LAUNCH_MAX_ROWS overrides; 0 = no limit)
+static int64_t launch_max_rows() {
+  static const int64_t v = [] {
+    const char* e = getenv("ERN_LAUNCH_MAX_ROWS");
+    const long long x = e ? atoll(e) : (1ll << 23);
+    return x <= 0 ? (1ll << 62) : static_cast<int64_t>(x);
+  }();
+  return v;
+}
+
 // test hook: ERN_FORCE_SINGLE_CTA=1 makes the tensor-core path use the 1-CTA kernel even for large batches
 static int force_single() {
   static const int v = [] {
@@ -420,6 +430,10 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
         end = begin * growth;
       }
       if (!first && mode == ERN_MODE_FP32 && end - begin > f32_rows_max) end = begin + f32_rows_max;
+      // Long launches let the query tiles that share a super tile drift apart (static round-robin items, ~775 per unit
+      // on a 58.7M-row launch): ncu then shows every gallery line fetched twice from DRAM (lts hit rate 87.5 % = 14/16).
+      // Cutting a range into launches of at most this many rows re-aligns the units every ~110 items.
+      if (!first && mode == ERN_MODE_BF16 && end - begin > launch_max_rows()) end = begin + launch_max_rows();
       if (end > n_rows) end = n_rows;
       sink.dense = first ? 1 : 0;
       sink.row_begin = begin;

@@ -6,6 +6,7 @@ Nothing here computes on the host or with torch ops -- torch is used for allocat
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -30,6 +31,8 @@ class _LaunchCounter:
 
 
 launch_counter = _LaunchCounter()
+# rows per tensor-core scoring launch (mirrors launch_max_rows() in csrc/ern_capi.cu, incl. its environment override)
+LAUNCH_MAX_ROWS = (lambda v: None if v <= 0 else v)(int(os.environ.get("ERN_LAUNCH_MAX_ROWS", str(1 << 23))))
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -76,18 +79,18 @@ def _phase_count(n_rows: int, k: int, growth: int, max_rows_per_launch: Optional
 
 
 def _sim_launches(nq: int, n_rows: int, k: int, growth: int, mode: int, device) -> int:
-    """Kernel launches of one ern_sim_topk call: per query batch one state-init launch plus a scoring and a
-    selection launch per schedule step."""
+    """Kernel launches of one ern_sim_topk call: per query batch one state-init launch plus, per schedule step, a
+    scoring launch and the selection (bf16 path: warp-per-query kernel + the block kernel for its leftovers)."""
     if nq == 0:
         return 0
     total = 0
     sms = torch.cuda.get_device_properties(device).multi_processor_count
     for q0 in range(0, nq, QUERY_BATCH):
         bq = min(QUERY_BATCH, nq - q0)
-        cap = None
+        cap = LAUNCH_MAX_ROWS
         if mode == MODE_FP32:
             cap = (sms // 2 if bq > 128 else sms) * SEG_CAP
-        total += 1 + 2 * _phase_count(n_rows, k, growth, cap)
+        total += 1 + (2 if mode == MODE_FP32 else 3) * _phase_count(n_rows, k, growth, cap)
     return total
 
 
