@@ -102,6 +102,35 @@ def test_accelerate_ern_swaps_reference_modules_and_keeps_weights():
     assert not model.Combiner_module.training                   # eval flag preserved
 
 
+def test_ern_checkpoint_carries_and_restores_clip_weights():
+    """The reference registers the CLIP model as a submodule of ImageCLIP / TextCLIP (models/clip_model.py:8,21), so
+    its fusion checkpoints carry the backbone under image_clip.clip_model.* / text_clip.clip_model.* and
+    load_state_dict restores it (run/test/test_fiq.py:148-149).  The B200 ERN keeps the backbone outside its own
+    parameters but must save and restore those keys the same way, and must say so when it cannot."""
+    import warnings
+    import fashionern_aaai2024_b200 as ern
+
+    class Clip(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(4, 4)
+
+    src_clip = Clip()
+    sd = ern.ERN(src_clip, 64, None).state_dict()
+    clip_keys = sorted(k for k in sd if "clip" in k)
+    assert clip_keys == ["image_clip.clip_model.lin.bias", "image_clip.clip_model.lin.weight",
+                         "text_clip.clip_model.lin.bias", "text_clip.clip_model.lin.weight"]
+    dst_clip = Clip()
+    assert not torch.equal(dst_clip.lin.weight, src_clip.lin.weight)
+    ern.ERN(dst_clip, 64, None).load_state_dict(sd)
+    assert torch.equal(dst_clip.lin.weight, src_clip.lin.weight) and torch.equal(dst_clip.lin.bias, src_clip.lin.bias)
+    # a stand-in that is not an nn.Module cannot take them: loud warning, the rest still loads
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ern.ERN(object(), 64, None).load_state_dict(sd)
+    assert any("CLIP backbone weights" in str(x.message) for x in w)
+
+
 def test_header_is_plain_c_and_links(tmp_path):
     """include/ern_b200.h must be consumable by a C compiler (the boundary is a C ABI, not C++) and every declared
     function must resolve against the built library."""
