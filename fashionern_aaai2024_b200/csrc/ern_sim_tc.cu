@@ -162,21 +162,17 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const int t1 = min(t0 + p.tiles_per_item, p.tiles_total);
         for (int t = t0; t < t1; ++t) {
           const int g_row = static_cast<int>(p.sink.row_begin) + t * kTileG + rank * kBlockG;
-          // (profiling knob, off by default) the query tiles of one super tile stream the same gallery tiles together:
-          // one unit per tile (rotating) pulls the tile into L2 a few tiles ahead of everybody's TMA loads.
-          if (p.prefetch_tiles > 0 && leader && ((t + p.prefetch_tiles) % p.n_qtiles) == qt && t + p.prefetch_tiles < t1) {
-            const int64_t prow = p.sink.row_begin + static_cast<int64_t>(t + p.prefetch_tiles) * kTileG;
-            int64_t nrows = p.gallery_rows - prow;
-            if (nrows > kTileG) nrows = kTileG;
-            if (nrows > 0)
-              ptx::prefetch_l2_bulk(p.gallery_base + prow * p.row_bytes, static_cast<uint32_t>(nrows * p.row_bytes));
-          }
+          // L2 prefetch of the gallery tile `prefetch_tiles` ahead, box by box in front of the matching loads (one
+          // unit per tile, rotating over the query tiles that share it): more bytes in flight than the 4-stage ring holds
+          const bool pf_on = p.prefetch_tiles > 0 && ((t + p.prefetch_tiles) % p.n_qtiles) == qt && t + p.prefetch_tiles < t1;
+          const int pf_row = g_row + p.prefetch_tiles * kTileG;
           for (int kb = 0; kb < p.num_kblocks; ++kb) {
             ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1, status, 2);
             const uint32_t full = ptx::smem_u32(&bars->full[stage]);
             if (leader) ptx::mbar_arrive_expect_tx(full, kTileBytes * kCta);
             if (kPair) ptx::tma_load_2d_pair(smem_b + stage * kTileBytes, &tmap_g, kb * kBlockK, g_row, ptx::mapa(full, 0));
             else       ptx::tma_load_2d(smem_b + stage * kTileBytes, &tmap_g, kb * kBlockK, g_row, full);
+            if (pf_on) ptx::tma_prefetch_2d(&tmap_g, kb * kBlockK, pf_row);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -488,11 +484,16 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& si
   Params p;
   static const int dbg = [] { const char* e = getenv("ERN_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
-  static const int pf = [] { const char* e = getenv("ERN_PREFETCH_TILES"); return e ? atoi(e) : 0; }();
+  // L2 prefetch distance in gallery tiles.  Default: 1 when a gallery tile has a single consumer (<= 256 queries: the
+  // HBM-bound / ridge regime, where the 4-stage ring alone keeps too few bytes in flight: 2.43 -> 2.35 ms at 128
+  // queries x 10M rows, 2.87 -> 2.79 ms at 256), 0 otherwise (no effect at >= 512 queries).  2 or more re-fetches
+  // lines that left L2 again (measured: 2.86 / 3.44 ms at distance 2 / 4).  ERN_PREFETCH_TILES overrides.
+  static const int pf_env = [] { const char* e = getenv("ERN_PREFETCH_TILES"); return e ? atoi(e) : -1; }();
   p.gallery_base = (ldg == dim) ? static_cast<const uint8_t*>(gallery) : nullptr;
   p.gallery_rows = gallery_rows;
   p.row_bytes = dim * 2;
-  p.prefetch_tiles = p.gallery_base ? pf : 0;
+  const int pf = pf_env >= 0 ? pf_env : (sink.nq <= (pair ? 2 * kBlockQ : kBlockQ) ? 1 : 0);
+  p.prefetch_tiles = pf;
   // ERN_TRACE_PTR: device address of a zeroed u64[8 * units] buffer owned by the profiling tool (tools/trace_sim.py)
   static unsigned long long* const trace = [] {
     const char* e = getenv("ERN_TRACE_PTR");

@@ -7,7 +7,7 @@ rows = [r for r in csv.reader(open(path)) if len(r) > 10]
 hdr = rows[0]
 ki, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("ID")
 items = [(int(r[ii]), r[ki][:70], float(r[vi].replace(",", ""))) for r in rows[1:]]
-ours = [x for x in items if "ern" in x[1] or "simtc" in x[1] or "small::" in x[1] or "gemmtc" in x[1]]
+ours = [x for x in items if any(t in x[1] for t in ("ern::", "simtc::", "small::", "gemmtc::", "combiner::", "visualsr::", "dvr::", "bbcloss::"))]
 for x in ours[-n:]:
     print(x)
 print("sum_us", sum(x[2] for x in ours[-n:]) / 1e3)
