@@ -97,19 +97,19 @@ def peaks():
 def profiled_traffic(queries, dim, rows_rank):
     """DRAM traffic of one profiled launch of the dominant kernel, read from the committed ncu summary
     (profiles/sim_topk_traffic.json, written by tools/ncu_traffic.py from an `ncu --set full` raw CSV).  Only
-    returned when the capture's workload matches this run (same batch, width, and a shard at least as large as the
-    profiled launch); otherwise null -- a literal from another configuration would be meaningless."""
+    returned when the capture's workload matches this run: same batch and width, and a launch of the size this run's
+    schedule actually issues (ops.LAUNCH_MAX_ROWS rows, which needs a shard at least that large); otherwise null -- a
+    literal from another configuration would be meaningless."""
+    from fashionern_aaai2024_b200 import ops
     path = os.path.join(ROOT, "profiles", "sim_topk_traffic.json")
-    if not os.path.exists(path):
+    if not os.path.exists(path) or ops.LAUNCH_MAX_ROWS is None or rows_rank < 2 * ops.LAUNCH_MAX_ROWS:
         return None
     with open(path) as f:
         entries = json.load(f)
-    best = None
     for e in entries:
-        if e["queries"] == queries and e["dim"] == dim and e["launch_rows"] <= rows_rank:
-            if best is None or e["launch_rows"] > best["launch_rows"]:
-                best = e
-    return best
+        if e["queries"] == queries and e["dim"] == dim and e["launch_rows"] == ops.LAUNCH_MAX_ROWS:
+            return e
+    return None
 
 
 class ClockSampler:
@@ -795,7 +795,7 @@ def main():
                 "frac": achieved / pk["bf16_sustained"],
                 "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
                 "traffic_algorithmic": tr["algorithmic_bytes"] if tr else None,
-                "traffic_basis": (f"one launch of {tr['launch_rows']} gallery rows x {tr['queries']} queries, ncu --set full "
+                "traffic_basis": (f"one launch of {tr['launch_rows']} gallery rows x {tr['queries']} queries (the launch size of this run's schedule), ncu --set full "
                                   f"({tr['source']}), read by bench.py from profiles/sim_topk_traffic.json") if tr else
                                  "no committed ncu capture matches this configuration",
                 "achieved_basis": "2*Q*rows*D FLOP of this rank's shard / CUDA-event time of the scoring call of one step "

@@ -32,7 +32,7 @@ class _LaunchCounter:
 
 launch_counter = _LaunchCounter()
 # rows per tensor-core scoring launch (mirrors launch_max_rows() in csrc/ern_capi.cu, incl. its environment override)
-LAUNCH_MAX_ROWS = (lambda v: None if v <= 0 else v)(int(os.environ.get("ERN_LAUNCH_MAX_ROWS", str(1 << 23))))
+LAUNCH_MAX_ROWS = (lambda v: None if v <= 0 else v)(int(os.environ.get("ERN_LAUNCH_MAX_ROWS", str(1 << 21))))
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:

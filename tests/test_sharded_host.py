@@ -35,8 +35,9 @@ def test_phase_schedule():
     # 256, 2k, 16k, 131k, 1M, 8.4M, 67M, 100M: a launch is exact for any number of rows ...
     assert _phase_count(1_000_000, 100, 8) == 5 and _phase_count(10_000_000, 100, 8) == 7
     assert _phase_count(100_000_000, 100, 8) == 8 and _phase_count(100_000_000, 100, 16) == 6
-    # ... but tensor-core launches are cut at 8.4M rows to keep the query tiles of a super tile aligned (L2 sharing)
-    assert _phase_count(100_000_000, 100, 8, 1 << 23) == 6 + -(-(100_000_000 - (1 << 23)) // (1 << 23))
+    # ... but tensor-core launches are cut at 2M rows: keeps the query tiles of a super tile aligned (L2 sharing) and
+    # the thresholds fresh on ordered galleries
+    assert _phase_count(100_000_000, 100, 8, 1 << 21) == 5 + 1 + -(-(100_000_000 - (1 << 20) - (1 << 21)) // (1 << 21))
     assert _phase_count(10_000, 100, 1) == 1 + -(-(10_000 - 256) // (2048 - 100))
     # the fp32 validation kernel never covers more rows than a query has candidate slots (74 x 256 here)
     assert _phase_count(100_000, 100, 8, 74 * 256) == 3 + -(-(100_000 - 16384) // (74 * 256))

@@ -1,8 +1,8 @@
 #!/bin/bash
-# ncu --set full of a dominant launch of the 100M-row step: the 7th scoring launch of a call covers gallery rows
-# [8.4M, 16.8M) = 8388608 rows x 4096 queries (launches are cut at 8.4M rows).  Raw CSV -> gpurun_out/ (copy the summary into profiles/).
+# ncu --set full of a typical launch of the 100M-row step: the 6th scoring launch of a call covers gallery rows
+# [1M, 3M) = 2097152 rows x 4096 queries (launches are cut at 2M rows).  Raw CSV -> gpurun_out/ (copy the summary into profiles/).
 mkdir -p gpurun_out
-ncu --set full --import-source on --clock-control none -k regex:sim_topk_tc -s 6 -c 1 -o gpurun_out/r02_sim_topk_100m -f \
+ncu --set full --import-source on --clock-control none -k regex:sim_topk_tc -s 5 -c 1 -o gpurun_out/r02_sim_topk_100m -f \
     python tools/quick_bench.py --n 100000000 --iters 1 > gpurun_out/ncu_full.log 2>&1
 echo "rc=$?"; tail -n 3 gpurun_out/ncu_full.log
 ncu -i gpurun_out/r02_sim_topk_100m.ncu-rep --page raw --csv > gpurun_out/r02_sim_topk_tc_100m_ncu_full_raw.csv 2>/dev/null
