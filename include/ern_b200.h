@@ -193,9 +193,10 @@ ERN_API int ern_dvr_encode(const ern_dvr_weights* w, int dim, int heads, int pat
  *   out_keys   (nullable) [nq,k] uint64 sortable (value,id) keys, the wire format of the multi-GPU
  *             candidate exchange (ern_topk_merge)
  *   growth    gallery-range growth factor of the launch schedule (>=2; 8 is the default): launch i covers rows
- *             [b, growth*b) starting from the exact k-th best of rows [0,b) as each query's threshold.  It is a cost
- *             knob only: candidate segments compact themselves inside the kernel, so the result is exact for ANY
- *             gallery order and any growth (growth == 1: fixed 1920-row steps, a test hook).
+ *             [b, growth*b) -- tensor-core launches at most 2M rows (environment ERN_LAUNCH_MAX_ROWS) -- starting
+ *             from the exact k-th best of rows [0,b) as each query's threshold.  It is a cost knob only: candidate
+ *             segments prune themselves inside the kernel, so the result is exact for ANY gallery order and any growth
+ *             (growth == 1: fixed (2048 - k)-row steps, a test hook).
  *   status_dev int32[4]: [0] != 0 => internal error (candidate storage inconsistent; never expected);
  *             [1..3] mbarrier watchdog diagnostics of a trapped launch.
  * MODE_BF16 requires dim % 64 == 0, dim <= 768 and 16-byte aligned rows.
