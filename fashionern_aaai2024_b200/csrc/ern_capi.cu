@@ -445,7 +445,7 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
           rc = simf32::launch(reinterpret_cast<const float*>(qbase), ldq, static_cast<const float*>(gallery_dev), ldg,
                               dim, sink, rank_by, st);
         } else {
-          rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, gallery_dev, n_rows, ldg, st);
+          rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, st);
         }
         if (rc) return rc;
       }

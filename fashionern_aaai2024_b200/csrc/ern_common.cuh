@@ -75,11 +75,12 @@ __device__ __forceinline__ float rank_value(float s) {
 //           the selection kernel); the first ("dense") launch stores every score of the first rows here instead.
 //   segs    [n_seg][seg_cap] keys : segment u has exactly ONE writer for a whole launch -- the persistent scoring unit
 //           (CTA pair / CTA) number u -- which appends with a private register cursor (no atomics) and publishes its
-//           count in seg_counts[q, u] when it leaves the query tile.  A segment never overflows: when fewer than 32
-//           free slots remain, the owning warp selects the segment's k best keys in place (warp_compact_segment), which
-//           also yields a tighter lower bound on the query's final k-th best value; the bound is shared with every
-//           other unit through thr_ord[q] (atomicMax on the order-preserving bits).  So a launch may cover any number
-//           of gallery rows in any order and stays exact -- gallery order only changes how often segments compact.
+//           count in seg_counts[q, u] when it leaves the query tile.  A segment never overflows: a gallery tile adds at
+//           most TILE_G <= 256 keys, and after every tile a segment holding more than seg_cap - TILE_G keys is pruned
+//           by its warp (warp_compact_segment) to the keys >= a pivot that at least k of them reach; the pivot is a
+//           valid lower bound of the query's final k-th best value and is shared with every other unit through
+//           thr_ord[q] (atomicMax on the order-preserving bits).  So a launch may cover any number of gallery rows in
+//           any order and stays exact -- gallery order only changes how often segments are pruned.
 //   thr_ord [1] : order-preserving bits of the current lower bound (f32_to_ordered(-inf) at start).
 // The fp32 validation kernel, whose blocks are not persistent, treats the n_seg * seg_cap slots of a query as one
 // segment with an atomic cursor in seg_counts[q, 0]; its launches are sized so that it cannot overflow.

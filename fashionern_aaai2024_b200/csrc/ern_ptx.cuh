@@ -105,10 +105,6 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, in
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
 }
-// contiguous global range -> L2 (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
-}
 
 // ---- tcgen05 ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -10,17 +10,19 @@
 //   D = 128 x TILE_G fp32 accumulator in TMEM, double buffered (2 x TILE_G columns),
 //   kPair: the two CTAs of a cluster issue ONE cta_group::2 UMMA of M = 256 (128 queries per CTA) by
 //          N = 256 (each CTA streams half of the gallery tile), halving shared-memory operand traffic.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer (leader CTA only
-// in a pair), warps 2..5 = epilogue; epilogue thread (quadrant, lane) owns one query row: it reads the
-// row's scores with tcgen05.ld (32 columns at a time), max-reduces them (FMNMX3) and only when the maximum reaches
+// Warp roles: warps 0..3 = epilogue (TMEM lane quadrant = warp id), warp 4 = TMA producer, warp 5 = TMEM allocator +
+// single-thread MMA issuer (leader CTA only in a pair); epilogue thread (quadrant, lane) owns one query row: it reads
+// the row's scores with tcgen05.ld (32 columns at a time), max-reduces them (FMNMX3) and only when the maximum reaches
 // the row's threshold walks a bit-mask of the 32 compares, appending survivors with a private cursor into the
-// list segment this persistent unit owns for that query (no atomics).  A segment that is about to fill up is compacted
-// in place by its warp to its k best keys, which also tightens the query's threshold for every unit (see
-// CandidateSink): a launch is exact for any gallery order and any number of rows.
+// segment this persistent unit owns for that query (no atomics; bursts take an out-of-line branch-free append).  A
+// tile adds at most TILE_G keys to a segment; after the tile's accumulator has been handed back, a segment that could
+// not take another whole tile is pruned in place by its warp (ern_compact.cuh), which also tightens the query's
+// threshold for every unit (see CandidateSink): a launch is exact for any gallery order and any number of rows.
 // Work items are (super tile of `tiles_per_item` gallery tiles, query tile), super-tile-major, dealt round-robin to
 // the persistent units: the query tiles of a batch sweep the same few super tiles at the same time and share them
 // through L2.  The epilogue is deliberately compact code (rolled chunk loop).
-// Environment knobs (profiling aids, read once): ERN_FORCE_SINGLE_CTA=1, ERN_PREFETCH_TILES=n, ERN_DEBUG_FLAGS.
+// Environment knobs (profiling aids, read once): ERN_FORCE_SINGLE_CTA=1, ERN_PREFETCH_TILES=n, ERN_TILES_PER_ITEM=n,
+// ERN_DEBUG_FLAGS, ERN_TRACE_PTR.
 #include "ern_common.cuh"
 #include "ern_compact.cuh"
 #include "ern_ptx.cuh"
@@ -50,9 +52,6 @@ struct Params {
   int tiles_total;      // gallery tiles of TILE_G rows in [row_begin, row_end)
   int tiles_per_item;   // gallery tiles per work item (super tile)
   int n_super;          // super tiles
-  const uint8_t* gallery_base;  // non-null iff gallery rows are contiguous (ld == dim): enables the L2 prefetch
-  int64_t gallery_rows;
-  int row_bytes;
   int prefetch_tiles;   // how many gallery tiles ahead of the TMA loads the L2 prefetch runs (0 = off)
   int debug;            // profiling aid (ERN_DEBUG_FLAGS): 1 = never take the append path, 2 = skip the TMEM reads
   unsigned long long* trace;   // profiling aid (ERN_TRACE_PTR): per unit 8 counters, see tools/trace_sim.py; null = off
@@ -478,7 +477,7 @@ int units_for(int64_t nq, int force_single, int sm_count) {
 
 // One launch of the tensor-core scoring kernel over shard rows [sink.row_begin, sink.row_end).
 int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
-           int force_single, int sm_count, const void* gallery, int64_t gallery_rows, int64_t ldg, cudaStream_t st) {
+           int force_single, int sm_count, cudaStream_t st) {
   const bool pair = !force_single && sink.nq > kBlockQ;
   const int tile_g = pair ? 256 : 128;
   Params p;
@@ -489,9 +488,6 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& si
   // queries x 10M rows, 2.87 -> 2.79 ms at 256), 0 otherwise (no effect at >= 512 queries).  2 or more re-fetches
   // lines that left L2 again (measured: 2.86 / 3.44 ms at distance 2 / 4).  ERN_PREFETCH_TILES overrides.
   static const int pf_env = [] { const char* e = getenv("ERN_PREFETCH_TILES"); return e ? atoi(e) : -1; }();
-  p.gallery_base = (ldg == dim) ? static_cast<const uint8_t*>(gallery) : nullptr;
-  p.gallery_rows = gallery_rows;
-  p.row_bytes = dim * 2;
   const int pf = pf_env >= 0 ? pf_env : (sink.nq <= (pair ? 2 * kBlockQ : kBlockQ) ? 1 : 0);
   p.prefetch_tiles = pf;
   // ERN_TRACE_PTR: device address of a zeroed u64[8 * units] buffer owned by the profiling tool (tools/trace_sim.py)
