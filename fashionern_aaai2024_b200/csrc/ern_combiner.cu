@@ -137,7 +137,7 @@ PackedView view_packed(const void* packed, int dim) {
   v.b1 = f + 8 * d;
   v.w2 = f + 16 * d;
   v.b2 = f + 24 * d;
-  // 16-byte aligned words after the vectors: grid-barrier / ticket counters of the small-batch kernel (zero between calls)
+  // 15 sets of 4 zeroed words behind the vectors: grid-barrier counters of the small-batch kernel (ern_combiner_small.cu)
   v.sync = reinterpret_cast<unsigned*>(const_cast<float*>(f + ((24 * d + 1 + 3) & ~size_t(3))));
   return v;
 }
@@ -157,7 +157,7 @@ int pack(const ern_combiner_weights* w, int dim, void* packed, cudaStream_t st) 
   ERN_CUDA(cudaMemcpyAsync(const_cast<float*>(v.b1), w->b_hid, 8 * d * 4, cudaMemcpyDeviceToDevice, st));
   ERN_CUDA(cudaMemcpyAsync(const_cast<float*>(v.w2), w->w_gate, 8 * d * 4, cudaMemcpyDeviceToDevice, st));
   ERN_CUDA(cudaMemcpyAsync(const_cast<float*>(v.b2), w->b_gate, 4, cudaMemcpyDeviceToDevice, st));
-  ERN_CUDA(cudaMemsetAsync(v.sync, 0, 16, st));
+  ERN_CUDA(cudaMemsetAsync(v.sync, 0, 240, st));
   return ERN_OK;
 }
 

@@ -7,8 +7,8 @@
 //   phase A   raw[B, 8D]  = relu([text | image] . [Wt ; Wi]^T + [bt ; bi])      fp32 inputs converted on the fly
 //   phase B   partial[B, c] = sum over the CTA's columns of relu(raw . W1^T + b1) * w2     (h[B, 8D] never exists)
 //   phase C   gate sigmoid, blend from the fp32 inputs, L2 normalise (CTA r handles row r after a second barrier)
-// ONE cooperative launch: the <= 148 CTAs are co-resident, a grid barrier (atomic counter in the packed-weights
-// buffer) separates the phases -- no launch gaps, no host round trips.
+// ONE cooperative launch: the <= 148 CTAs are co-resident, grid barriers (atomic counters behind the packed weights,
+// one of 15 sets per call, left at zero by the last CTA) separate the phases -- no launch gaps, no host round trips.
 // Both GEMMs split the OUTPUT COLUMNS over the CTAs (32-48 columns each, so that one wave of <= 148 CTAs covers the
 // matrix) and the K range over the 8 warps of a CTA: every weight byte is read exactly once from HBM by exactly one
 // warp with 16-byte streaming loads, several K blocks in flight per warp (64-100 KB per SM); no cross-CTA reduction, no
@@ -237,7 +237,7 @@ struct HeadArgs {
   PackedView pv;
   __nv_bfloat16* raw;        // [rows, 8D] scratch
   float* partial;            // [rows, gridDim.x] scratch
-  unsigned* sync;            // [2] zero between calls (lives in the packed-weights buffer)
+  unsigned* sync;            // [3] zero between calls (one of 15 sets behind the packed weights)
   float* out;                // [rows, D] or null
   __nv_bfloat16* out_bf16;   // [rows, ldb] or null
   int64_t ldb;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
     if (a.gate && threadIdx.x == 0) a.gate[r] = s;
   }
   STAMP(5);
-  // the CTA that leaves last puts the three counters back to zero for the next call on this stream
+  // the CTA that leaves last puts the three counters back to zero for the next call that draws this set
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();

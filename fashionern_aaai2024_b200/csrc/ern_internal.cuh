@@ -40,7 +40,7 @@ namespace combiner {
 struct PackedView {
   const __nv_bfloat16 *wt, *wi, *w1;
   const float *bt, *bi, *b1, *w2, *b2;
-  unsigned* sync;   // [4] counters of the small-batch kernel, zero between calls
+  unsigned* sync;   // 15 x [4] zeroed counter sets of the small-batch kernel
 };
 PackedView view_packed(const void* packed, int dim);
 int launch_finalize(const float* image, const float* text, int64_t rows, int dim, const float* partial, int n_tiles,

@@ -73,6 +73,29 @@ def test_small_batches_weight_streaming_path(cuda_device, dim, rows):
     assert torch.isfinite(out).all()
 
 
+def test_small_batch_head_on_concurrent_streams(cuda_device):
+    """The fused small-batch kernel synchronises its CTAs through counters that live behind the packed weights (15
+    rotating, self-resetting sets): forwards of ONE module issued on several streams at once must neither hang nor mix
+    results."""
+    dim = 640
+    m = make(dim, 33, "bf16", cuda_device)
+    xs = [(syn.features(100 + i, 32, dim).to(cuda_device), syn.features(200 + i, 32, dim, unit=True).to(cuda_device))
+          for i in range(4)]
+    with torch.no_grad():
+        want = [m(a, b).clone() for a, b in xs]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream(cuda_device) for _ in range(4)]
+        outs = [[] for _ in range(4)]
+        for rep in range(12):
+            for i, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    outs[i].append(m(*xs[i]))
+        torch.cuda.synchronize()
+    for i in range(4):
+        for o in outs[i]:
+            assert torch.equal(o, want[i])
+
+
 def test_dvr_call_site_inputs(cuda_device):
     # the three query-side call sites (models/fusion_model.py:52-54) with the inputs the reference recorded
     z, meta = load_golden("fiq640")
