@@ -276,17 +276,19 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
     const float* __restrict__ x = (static_cast<int>(blockIdx.x) * kCols < proj) ? a.text : a.image;
     const int chunks_per_row = a.dim / 8;
     const int total = 16 * kMTiles * chunks_per_row;
-    // eight 8-element chunks per thread and pass: all their loads are in flight before the first conversion
-    for (int c0 = threadIdx.x; c0 < total; c0 += 8 * kThreads) {
-      uint32_t v[8][4];
+    // twelve 8-element chunks per thread and pass (one pass covers 32 rows x 640): all their loads are in flight before
+    // the first conversion
+    constexpr int kBatch = 12;
+    for (int c0 = threadIdx.x; c0 < total; c0 += kBatch * kThreads) {
+      uint32_t v[kBatch][4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const int cc = c0 + u * kThreads;
         const int r = cc / chunks_per_row, c = cc - r * chunks_per_row;
         load8_act(x + static_cast<int64_t>(r < a.rows ? r : 0) * a.dim + c * 8, cc < total && r < a.rows, v[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const int cc = c0 + u * kThreads;
         const int r = cc / chunks_per_row, c = cc - r * chunks_per_row;
         if (cc < total)
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   __syncthreads();
   if (threadIdx.x == 0) {
     atomicAdd(&a.sync[0], 1u);
-    while (ld_acquire(&a.sync[0]) < static_cast<unsigned>(n_ctas)) __nanosleep(32);
+    while (ld_acquire(&a.sync[0]) < static_cast<unsigned>(n_ctas)) {}
   }
   __syncthreads();
   STAMP(2);
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   if (threadIdx.x == 0) {
     atomicAdd(&a.sync[1], 1u);
     if (finisher)
-      while (ld_acquire(&a.sync[1]) < static_cast<unsigned>(n_ctas)) __nanosleep(32);
+      while (ld_acquire(&a.sync[1]) < static_cast<unsigned>(n_ctas)) {}
   }
   __syncthreads();
   STAMP(4);
