@@ -20,9 +20,12 @@ def main():
     dev = torch.device("cuda", 0)
     worst = {}
 
+    failures = []
+
     def note(name, err, tol):
         worst[name] = max(worst.get(name, 0.0), err / tol)
-        assert err <= tol, (name, err, tol)
+        if err > tol:                                  # keep going: the summary lists every case over its tolerance
+            failures.append((name, err, tol))
 
     for it in range(24):
         dim = int(rng.choice([512, 640]))
@@ -75,7 +78,8 @@ def main():
             out = m(patches.to(dev), tokens.to(dev), rg.to(dev), tg.to(dev)).cpu()
         ref = orc.dvr_forward(sd, patches, tokens, rg, tg)
         note(f"dvr/{mode}", float((out - ref).norm(dim=-1).max()), 1e-2 if mode == "bf16" else 2e-5)
-    print("SOAK_OK", {k: round(v, 3) for k, v in sorted(worst.items())}, "(worst error as a fraction of its tolerance)")
+    print("SOAK_OK" if not failures else "SOAK_OVER_TOLERANCE", {k: round(v, 3) for k, v in sorted(worst.items())},
+          "(worst error as a fraction of its tolerance)", failures)
 
 
 if __name__ == "__main__":
