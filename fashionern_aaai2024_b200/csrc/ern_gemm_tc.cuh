@@ -58,6 +58,7 @@ struct Params {
   float* diag;            // [M]                kEpiLse
   const float* rowvec;    // [M]                kEpiSmGradRow: per-row logsumexp
   const float* gscale;    // [1] device scalar multiplied into beta (upstream gradient), nullable
+  int f16_operands;       // 1: A and W hold fp16 instead of bf16 (same 2-byte layout, same MMA rate; VisualSR)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -189,7 +190,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = unit; t < total; t += n_units) {
         const bool narrow = kPair && (t % n_tiles) * kBlockN + kBlockN / 2 >= p.n;
-        const uint32_t idesc = narrow ? idesc_half : idesc_full;
+        // (A / B format fields: 1 = bf16, 0 = fp16)
+        const uint32_t idesc = (narrow ? idesc_half : idesc_full) & (p.f16_operands ? ~((1u << 7) | (1u << 10)) : ~0u);
         ptx::mbar_wait(ptx::smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1, nullptr, 12);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBlockN;

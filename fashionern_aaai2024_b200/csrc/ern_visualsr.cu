@@ -11,6 +11,8 @@
 //
 // The [B*13, D] x [D, D] GEMM runs on the tensor cores (ern_gemm_tc.cuh); its epilogue applies the affine, tanh and
 // the product with c[b,:] = g_emb[b,:] * wc and row-reduces, so l_emb never reaches HBM.
+#include <cuda_fp16.h>
+
 #include "ern_gemm_tc.cuh"
 
 namespace ern {
@@ -18,10 +20,23 @@ namespace visualsr {
 
 constexpr int kMaxPatches = 32;
 
+// The tensor-core path of VisualSR feeds its GEMMs FP16 operands, not bf16: the 13-way softmax of the attention
+// logits amplifies operand rounding (bf16, 8 mantissa bits: worst output row 1.06e-2 on N(0,1) synthetic patches, a CPU
+// emulation attributes ~5e-3 each to the rounding of the patches, of W_local and of the global branch); fp16 has 11
+// bits and runs at the same tcgen05 rate (kind::f16 takes either).  CLIP patch features and Xavier weights sit well
+// inside fp16's range; the conversion saturates at +-65504 instead of producing infinities.
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ __half to_f16(float a) { return __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)); }
+
 // one warp per row b: mean over patches (+ bf16 copies of the patch matrix and of the mean for the GEMMs); HBM-bound
 __global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, int patches, int dim,
-                               float* __restrict__ mean_f32, __nv_bfloat16* __restrict__ mean_b,
-                               __nv_bfloat16* __restrict__ local_b) {
+                               float* __restrict__ mean_f32, __half* __restrict__ mean_b,
+                               __half* __restrict__ local_b) {
   const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= rows) return;
@@ -34,17 +49,14 @@ __global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, in
         const float4 v = *reinterpret_cast<const float4*>(x + p * dim + d);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         if (local_b) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-          uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-          *reinterpret_cast<uint2*>(local_b + (b * patches + p) * dim + d) = pk;
+          *reinterpret_cast<uint2*>(local_b + (b * patches + p) * dim + d) =
+              make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
         }
       }
       const float4 m = make_float4(s.x / inv, s.y / inv, s.z / inv, s.w / inv);
       if (mean_f32) *reinterpret_cast<float4*>(mean_f32 + b * dim + d) = m;
       if (mean_b) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(m.x, m.y), hi = __floats2bfloat162_rn(m.z, m.w);
-        *reinterpret_cast<uint2*>(mean_b + b * dim + d) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        *reinterpret_cast<uint2*>(mean_b + b * dim + d) = make_uint2(pack_f16x2(m.x, m.y), pack_f16x2(m.z, m.w));
       }
     }
     return;
@@ -54,11 +66,11 @@ __global__ void prepare_kernel(const float* __restrict__ local, int64_t rows, in
     for (int p = 0; p < patches; ++p) {
       const float v = x[p * dim + d];
       s += v;
-      if (local_b) local_b[(b * patches + p) * dim + d] = __float2bfloat16_rn(v);
+      if (local_b) local_b[(b * patches + p) * dim + d] = to_f16(v);
     }
     const float m = s / inv;
     if (mean_f32) mean_f32[b * dim + d] = m;
-    if (mean_b) mean_b[b * dim + d] = __float2bfloat16_rn(m);
+    if (mean_b) mean_b[b * dim + d] = to_f16(m);
   }
 }
 
@@ -196,7 +208,7 @@ __global__ void finalize_kernel(const float* __restrict__ local, int64_t rows, i
 template <int kP, int kIters>
 __global__ void __launch_bounds__(256)
 prepare_fixed_kernel(const float* __restrict__ local, int64_t rows, float* __restrict__ mean_f32,
-                     __nv_bfloat16* __restrict__ mean_b, __nv_bfloat16* __restrict__ local_b) {
+                     __half* __restrict__ mean_b, __half* __restrict__ local_b) {
   constexpr int kDim = 128 * kIters;
   const int64_t b = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -212,24 +224,22 @@ prepare_fixed_kernel(const float* __restrict__ local, int64_t rows, float* __res
     for (int p = 0; p < kP; ++p) {
       s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w;
       if (local_b) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v[p].x, v[p].y), hi = __floats2bfloat162_rn(v[p].z, v[p].w);
         *reinterpret_cast<uint2*>(local_b + (b * kP + p) * kDim + lane * 4 + it * 128) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            make_uint2(pack_f16x2(v[p].x, v[p].y), pack_f16x2(v[p].z, v[p].w));
       }
     }
     const float inv = static_cast<float>(kP);
     const float4 m = make_float4(s.x / inv, s.y / inv, s.z / inv, s.w / inv);
     if (mean_f32) *reinterpret_cast<float4*>(mean_f32 + b * kDim + lane * 4 + it * 128) = m;
     if (mean_b) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(m.x, m.y), hi = __floats2bfloat162_rn(m.z, m.w);
       *reinterpret_cast<uint2*>(mean_b + b * kDim + lane * 4 + it * 128) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          make_uint2(pack_f16x2(m.x, m.y), pack_f16x2(m.z, m.w));
     }
   }
 }
 
 static void launch_prepare_sr(const float* local, int64_t rows, int patches, int dim, float* mean_f32,
-                              __nv_bfloat16* mean_b, __nv_bfloat16* local_b, cudaStream_t st) {
+                              __half* mean_b, __half* local_b, cudaStream_t st) {
   const int blocks = cdiv(rows * 32, 256);
   const bool aligned = ((reinterpret_cast<uintptr_t>(local) | reinterpret_cast<uintptr_t>(mean_f32) |
                          reinterpret_cast<uintptr_t>(mean_b) | reinterpret_cast<uintptr_t>(local_b)) & 15u) == 0;
@@ -318,12 +328,18 @@ constexpr int kTcBlockN = 256;   // CTA-pair tiles; a ragged last column tile (D
 
 size_t packed_bytes(int dim) { return al(static_cast<size_t>(dim) * dim * 2) * 2 + 256; }
 
+__global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = to_f16(src[i]);
+}
+
 int pack(const ern_visualsr_weights* w, int dim, void* packed, cudaStream_t st) {
   const int64_t n = static_cast<int64_t>(dim) * dim;
   uint8_t* p = static_cast<uint8_t*>(packed);
-  int rc = combiner::launch_cast_bf16(w->w_local, p, n, st);
-  if (rc) return rc;
-  return combiner::launch_cast_bf16(w->w_global, p + al(n * 2), n, st);
+  cast_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(w->w_local, reinterpret_cast<__half*>(p), n);
+  cast_f16_kernel<<<cdiv(n, 256), 256, 0, st>>>(w->w_global, reinterpret_cast<__half*>(p + al(n * 2)), n);
+  ERN_CUDA(cudaGetLastError());
+  return ERN_OK;
 }
 
 size_t workspace_bytes(int64_t rows, int patches, int dim, int mode) {
@@ -356,8 +372,8 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
     return ERN_OK;
   }
   // ---- tensor-core path
-  __nv_bfloat16* local_b = reinterpret_cast<__nv_bfloat16*>(ws);
-  __nv_bfloat16* mean_b = reinterpret_cast<__nv_bfloat16*>(ws + al(r * P * d * 2));
+  __half* local_b = reinterpret_cast<__half*>(ws);            // fp16 operands (see pack_f16x2)
+  __half* mean_b = reinterpret_cast<__half*>(ws + al(r * P * d * 2));
   float* cvec = reinterpret_cast<float*>(ws + al(r * P * d * 2) + al(r * d * 2));
   float* partial = reinterpret_cast<float*>(ws + al(r * P * d * 2) + al(r * d * 2) + al(r * d * 4));
   const int n_tiles = gemmtc::n_tiles_of<kTcBlockN>(dim);
@@ -382,6 +398,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
   g.shift = w->bn_global_shift;
   g.out_f32 = cvec;
   g.ldo = dim;
+  g.f16_operands = 1;
   if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrGlobal, true>(t_mean, t_wg, g, sm_count, st))) return rc;
   gemmtc::Params l{};
   l.m = rows * patches;
@@ -393,6 +410,7 @@ int forward(const ern_visualsr_weights* w, int dim, int patches, int mode, const
   l.cvec = cvec;
   l.patches = patches;
   l.partial = partial;
+  l.f16_operands = 1;
   if ((rc = gemmtc::launch<kTcBlockN, gemmtc::kEpiSrLocal, true>(t_local, t_wl, l, sm_count, st))) return rc;
   launch_finalize_sr(local, rows, patches, dim, partial, n_tiles, w->b_common, out, st);
   ERN_CUDA(cudaGetLastError());

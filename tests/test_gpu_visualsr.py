@@ -9,7 +9,9 @@ from helpers import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-5, "bf16": 1e-2}
+# "bf16" = the 16-bit tensor-core mode; VisualSR feeds its GEMMs fp16 operands there (the 13-way softmax amplifies operand
+# rounding: with bf16 operands the worst row of a random case reached 1.06e-2), observed worst 1.1e-3
+TOL = {"fp32": 1e-5, "bf16": 2.5e-3}
 
 
 def make(dim, seed, mode, dev):
