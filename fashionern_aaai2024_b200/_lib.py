@@ -18,7 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ERN_B200_LIB") or os.path.join(_HERE, "libern_b200.so")
 
 MODE_BF16, MODE_FP32 = 0, 1
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+NORM_OUT_F16 = 2          # ern_l2norm_rows: OR into `normalize` for an fp16 (instead of bf16) 16-bit output
 RANK_SIMILARITY, RANK_REFERENCE = 0, 1
 MAX_K, SEG_CAP, SORT_CAP, QUERY_BATCH, DENSE_ROWS = 128, 512, 2048, 4096, 256
 

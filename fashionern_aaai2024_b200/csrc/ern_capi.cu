@@ -339,8 +339,9 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
   ERN_REQUIRE(out_scores_dev || out_ids_dev || out_keys_dev || peer_keys_dev, "no output requested");
   ERN_REQUIRE(!peer_keys_dev || (world >= 1 && rank >= 0 && rank < world), "bad world/rank for the fused exchange");
   ERN_REQUIRE(id_offset >= 0 && id_offset + n_rows <= 0x7FFFFFFFll, "global ids must fit int32");
-  ERN_REQUIRE((mode == ERN_MODE_FP32 && dtype == ERN_DTYPE_F32) || (mode == ERN_MODE_BF16 && dtype == ERN_DTYPE_BF16),
-              "mode/dtype mismatch: FP32 mode takes f32 features, BF16 mode takes bf16 features");
+  ERN_REQUIRE((mode == ERN_MODE_FP32 && dtype == ERN_DTYPE_F32) ||
+                  (mode == ERN_MODE_BF16 && (dtype == ERN_DTYPE_BF16 || dtype == ERN_DTYPE_F16)),
+              "mode/dtype mismatch: FP32 mode takes f32 features, BF16 (tensor-core) mode takes bf16 or fp16 features");
   if (nq == 0) return ERN_OK;
   ERN_REQUIRE(queries_dev && (gallery_dev || n_rows == 0) && ldq >= dim && ldg >= dim, "bad feature matrices");
   if (workspace_bytes < ern_sim_topk_workspace_bytes(nq, dim, mode) || !workspace_dev) {
@@ -445,7 +446,7 @@ static int sim_topk_impl(const void* queries_dev, int64_t nq, int64_t ldq, const
           rc = simf32::launch(reinterpret_cast<const float*>(qbase), ldq, static_cast<const float*>(gallery_dev), ldg,
                               dim, sink, rank_by, st);
         } else {
-          rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, st);
+          rc = simtc::launch(tq, tg, sink, dim, rank_by, force_single(), di.sm_count, dtype == ERN_DTYPE_F16, st);
         }
         if (rc) return rc;
       }
@@ -527,7 +528,7 @@ int ern_cirr_subset_recall(const void* queries_dev, int64_t nq, int64_t ldq, con
   if (rc) return rc;
   ERN_REQUIRE(queries_dev && gallery_dev && members_dev && reference_id_dev && target_id_dev && ks && counts_dev,
               "bad arguments");
-  ERN_REQUIRE(dtype == ERN_DTYPE_F32 || dtype == ERN_DTYPE_BF16, "bad dtype");
+  ERN_REQUIRE(dtype == ERN_DTYPE_F32 || dtype == ERN_DTYPE_BF16 || dtype == ERN_DTYPE_F16, "bad dtype");
   return launch_cirr_subset(queries_dev, nq, ldq, gallery_dev, n_rows, ldg, dim, dtype, members_dev, m,
                             reference_id_dev, target_id_dev, rank_by, ks, nk, counts_dev, rank_dev,
                             static_cast<cudaStream_t>(stream));
@@ -540,7 +541,7 @@ int ern_gather_scores(const void* queries_dev, int64_t nq, int64_t ldq, const vo
   int rc = current_device(&di);
   if (rc) return rc;
   ERN_REQUIRE(queries_dev && (gallery_dev || n_rows == 0) && ids_dev && out_scores_dev, "bad arguments");
-  ERN_REQUIRE(dtype == ERN_DTYPE_F32 || dtype == ERN_DTYPE_BF16, "bad dtype");
+  ERN_REQUIRE(dtype == ERN_DTYPE_F32 || dtype == ERN_DTYPE_BF16 || dtype == ERN_DTYPE_F16, "bad dtype");
   return launch_gather_scores(queries_dev, nq, ldq, gallery_dev, n_rows, ldg, dim, dtype, id_offset, ids_dev, m,
                               out_scores_dev, static_cast<cudaStream_t>(stream));
 }

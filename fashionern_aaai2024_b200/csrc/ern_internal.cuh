@@ -33,7 +33,7 @@ namespace simtc {
 int make_tmap_bf16_rows(CUtensorMap* map, const void* base, int64_t rows, int dim, int64_t ld_elems);
 int units_for(int64_t nq, int force_single, int sm_count);
 int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
-           int force_single, int sm_count, cudaStream_t st);
+           int force_single, int sm_count, bool f16_operands, cudaStream_t st);
 }
 namespace combiner {
 // views into the buffer filled by ern_combiner_pack: bf16 K-major weight matrices + fp32 vectors

@@ -53,6 +53,7 @@ struct Params {
   int tiles_per_item;   // gallery tiles per work item (super tile)
   int n_super;          // super tiles
   int prefetch_tiles;   // how many gallery tiles ahead of the TMA loads the L2 prefetch runs (0 = off)
+  int f16_operands;     // 1: queries and gallery hold fp16 instead of bf16 (same layout, same MMA rate)
   int debug;            // profiling aid (ERN_DEBUG_FLAGS): 1 = never take the append path, 2 = skip the TMEM reads
   unsigned long long* trace;   // profiling aid (ERN_TRACE_PTR): per unit 8 counters, see tools/trace_sim.py; null = off
 };
@@ -181,7 +182,8 @@ sim_topk_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ================================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(kBlockQ * kCta, kTileG);
+      // (A / B format fields of the instruction descriptor: 1 = bf16, 0 = fp16)
+      const uint32_t idesc = ptx::idesc_bf16_f32(kBlockQ * kCta, kTileG) & (p.f16_operands ? ~((1u << 7) | (1u << 10)) : ~0u);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, it = 0;
       // cycle accounting of the issuing thread (ERN_TRACE_PTR): total cycles and tiles cost nothing inside the loop;
       // the per-wait split perturbs the issue loop by ~8 % and is compiled in only with -DERN_SIM_TRACE_WAITS
@@ -485,12 +487,13 @@ int units_for(int64_t nq, int force_single, int sm_count) {
 
 // One launch of the tensor-core scoring kernel over shard rows [sink.row_begin, sink.row_end).
 int launch(const CUtensorMap& tq, const CUtensorMap& tg, const CandidateSink& sink, int dim, int rank_by,
-           int force_single, int sm_count, cudaStream_t st) {
+           int force_single, int sm_count, bool f16_operands, cudaStream_t st) {
   const bool pair = !force_single && sink.nq > kBlockQ;
   const int tile_g = pair ? 256 : 128;
   Params p;
   static const int dbg = [] { const char* e = getenv("ERN_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
   p.debug = dbg;
+  p.f16_operands = f16_operands ? 1 : 0;
   // L2 prefetch distance in gallery tiles.  Default: 1 when a gallery tile has a single consumer (<= 256 queries: the
   // HBM-bound / ridge regime, where the 4-stage ring alone keeps too few bytes in flight: 2.43 -> 2.35 ms at 128
   // queries x 10M rows, 2.87 -> 2.79 ms at 256), 0 otherwise (no effect at >= 512 queries).  2 or more re-fetches

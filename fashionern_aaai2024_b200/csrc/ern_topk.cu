@@ -2,6 +2,7 @@
 // All of them are small HBM/latency-bound integer or reduction kernels next to the scoring GEMM.
 #include "ern_internal.cuh"
 #include "ern_select.cuh"
+#include <cuda_fp16.h>
 
 namespace ern {
 
@@ -542,6 +543,8 @@ template <>
 __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) {
   return __bfloat162float(p[i]);
 }
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
 
 constexpr int kMaxMembers = 8;
 
@@ -654,6 +657,10 @@ int launch_gather_scores(const void* queries, int64_t nq, int64_t ldq, const voi
     gather_scores_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(queries), nq, ldq,
                                                       static_cast<const float*>(gallery), n_rows, ldg, dim, id_offset,
                                                       ids, m, out);
+  else if (dtype == ERN_DTYPE_F16)
+    gather_scores_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(queries), nq, ldq,
+                                                       static_cast<const __half*>(gallery), n_rows, ldg, dim, id_offset,
+                                                       ids, m, out);
   else
     gather_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(queries), nq, ldq,
                                                               static_cast<const __nv_bfloat16*>(gallery), n_rows, ldg,
@@ -692,6 +699,10 @@ int launch_cirr_subset(const void* queries, int64_t nq, int64_t ldq, const void*
       cirr_subset_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(queries), nq, ldq,
                                                       static_cast<const float*>(gallery), n_rows, ldg, dim, members,
                                                       m, ref_id, tgt_id, rank_by, kl, counts, rank_out);
+    else if (dtype == ERN_DTYPE_F16)
+      cirr_subset_kernel<__half><<<grid, 256, 0, st>>>(
+          static_cast<const __half*>(queries), nq, ldq, static_cast<const __half*>(gallery), n_rows, ldg, dim, members,
+          m, ref_id, tgt_id, rank_by, kl, counts, rank_out);
     else
       cirr_subset_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
           static_cast<const __nv_bfloat16*>(queries), nq, ldq, static_cast<const __nv_bfloat16*>(gallery), n_rows,
@@ -705,8 +716,8 @@ int launch_cirr_subset(const void* queries, int64_t nq, int64_t ldq, const void*
 // Row L2-normalise (F.normalize eps 1e-12) + optional bf16 cast; one warp per row, HBM-bound.
 // ------------------------------------------------------------------------------------------------------
 __global__ void l2norm_rows_kernel(const float* __restrict__ x, int64_t rows, int dim, int64_t ldx, int normalize,
-                                   float* __restrict__ of, int64_t ldf, __nv_bfloat16* __restrict__ ob,
-                                   int64_t ldb) {
+                                   float* __restrict__ of, int64_t ldf, uint16_t* __restrict__ ob, int64_t ldb,
+                                   int out_f16) {
   const int64_t r = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -721,15 +732,16 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, int64_t rows, in
   for (int d = lane; d < dim; d += 32) {
     const float v = normalize ? xr[d] / denom : xr[d];
     if (of) of[r * ldf + d] = v;
-    if (ob) ob[r * ldb + d] = __float2bfloat16_rn(v);
+    if (ob) ob[r * ldb + d] = out_f16 ? __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)))
+                                      : __bfloat16_as_ushort(__float2bfloat16_rn(v));
   }
 }
 
 int launch_l2norm_rows(const float* x, int64_t rows, int dim, int64_t ldx, int normalize, float* of, int64_t ldf,
                        void* ob, int64_t ldb, cudaStream_t st) {
   if (rows <= 0) return ERN_OK;
-  l2norm_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(x, rows, dim, ldx, normalize, of, ldf,
-                                                           static_cast<__nv_bfloat16*>(ob), ldb);
+  l2norm_rows_kernel<<<cdiv(rows * 32, 256), 256, 0, st>>>(x, rows, dim, ldx, normalize & 1, of, ldf,
+                                                           static_cast<uint16_t*>(ob), ldb, (normalize & ERN_NORM_OUT_F16) ? 1 : 0);
   ERN_CUDA(cudaGetLastError());
   return ERN_OK;
 }

@@ -22,8 +22,10 @@ no [Q,N] index matrix crosses to the host and no numpy string gather/compare hap
   CIRR subset recall .......... ern_cirr_subset_recall   (test_cirr.py:64-66,76-78)
 
 Names (Python strings) are factorised once on the host into int32 ids; only hit counts (a few ints) come
-back from the device.  ``precision`` selects the arithmetic: "bf16" (tensor cores, default) or "fp32"
-(validation mode that reproduces the reference's fp32 ranking of ``1 - s`` including its rounding ties).
+back from the device.  ``precision`` selects the arithmetic: "bf16" (tensor cores, default), "fp16" (the same
+tensor-core kernel on fp16-rounded operands: 11 mantissa bits instead of 8 at the same rate, safe for the unit-norm
+features this tail scores) or "fp32" (validation mode that reproduces the reference's fp32 ranking of ``1 - s``
+including its rounding ties).
 """
 from __future__ import annotations
 
@@ -37,13 +39,15 @@ from . import ops
 from ._lib import MODE_BF16, MODE_FP32, RANK_REFERENCE, ErnError, require_cuda
 
 _PRECISION = "bf16"
+_PRECISIONS = ("bf16", "fp16", "fp32")
 _TOKENIZER_FACTORY: Optional[Callable[[str], Callable]] = None
 
 
 def set_precision(precision: str) -> None:
-    """Default arithmetic of the tail: 'bf16' (product path) or 'fp32' (validation mode)."""
+    """Default arithmetic of the tail: 'bf16' (product path), 'fp16' (same kernel, fp16 operands) or 'fp32'
+    (validation mode)."""
     global _PRECISION
-    if precision not in ("bf16", "fp32"):
+    if precision not in _PRECISIONS:
         raise ErnError(f"unknown precision {precision!r}")
     _PRECISION = precision
 
@@ -180,16 +184,19 @@ def prepare_gallery(index_features: torch.Tensor, index_local_features, model, d
 def _operands(pred: torch.Tensor, gallery: torch.Tensor, precision: str):
     pred = pred.float().contiguous()
     gallery = gallery.float().contiguous()
+    if precision not in _PRECISIONS:
+        raise ErnError(f"unknown precision {precision!r}")
     if precision == "fp32":
         return pred, gallery, MODE_FP32
-    # bf16 operands for the tensor-core path; pad D up to a multiple of 64 with zeros (cosine unchanged)
+    # 16-bit operands for the tensor-core path; pad D up to a multiple of 64 with zeros (cosine unchanged)
     d = pred.shape[1]
     dp = (d + 63) // 64 * 64
     if dp != d:
         pred = torch.nn.functional.pad(pred, (0, dp - d))
         gallery = torch.nn.functional.pad(gallery, (0, dp - d))
-    _, qb = ops.l2norm_rows(pred, normalize=False, want_f32=False, want_bf16=True)
-    _, gb = ops.l2norm_rows(gallery, normalize=False, want_f32=False, want_bf16=True)
+    f16 = precision == "fp16"
+    _, qb = ops.l2norm_rows(pred, normalize=False, want_f32=False, want_bf16=not f16, want_f16=f16)
+    _, gb = ops.l2norm_rows(gallery, normalize=False, want_f32=False, want_bf16=not f16, want_f16=f16)
     return qb, gb, MODE_BF16
 
 

@@ -12,8 +12,8 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib as L
-from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F32, MODE_BF16, MODE_FP32, QUERY_BATCH, RANK_REFERENCE,
-                   RANK_SIMILARITY, SEG_CAP, SORT_CAP, ErnError)
+from ._lib import (DENSE_ROWS, DTYPE_BF16, DTYPE_F16, DTYPE_F32, MODE_BF16, MODE_FP32, QUERY_BATCH, RANK_REFERENCE,
+                   RANK_SIMILARITY, SEG_CAP, SORT_CAP, NORM_OUT_F16, ErnError)
 
 __all__ = ["l2norm_rows", "sim_topk", "sim_topk_exchange", "topk_merge", "recall_at_k", "cirr_subset_recall", "gather_scores",
            "cirr_subset_from_scores", "bbc_loss_forward", "bbc_loss_backward", "launch_counter"]
@@ -31,6 +31,20 @@ class _LaunchCounter:
 
 
 launch_counter = _LaunchCounter()
+_DTYPE_OF = {torch.float32: DTYPE_F32, torch.bfloat16: DTYPE_BF16, torch.float16: DTYPE_F16}
+
+
+def _feature_dtype(q: torch.Tensor, g: torch.Tensor, mode: Optional[int] = None) -> int:
+    """ERN_DTYPE_* of a (queries, gallery) pair: both float32 (fp32 validation mode) or both the same 16-bit type
+    (tensor-core mode: bf16, or fp16 for 3 more mantissa bits at the same tcgen05 rate)."""
+    if q.dtype != g.dtype or q.dtype not in _DTYPE_OF:
+        raise ErnError(f"queries/gallery must both be float32, bfloat16 or float16, got {q.dtype} / {g.dtype}")
+    if mode is not None and (mode == MODE_FP32) != (q.dtype == torch.float32):
+        want = "float32" if mode == MODE_FP32 else "bfloat16 or float16"
+        raise ErnError(f"mode {mode} takes {want} features, got queries {q.dtype} / gallery {g.dtype}")
+    return _DTYPE_OF[q.dtype]
+
+
 # rows per tensor-core scoring launch (mirrors launch_max_rows() in csrc/ern_capi.cu, incl. its environment override)
 LAUNCH_MAX_ROWS = (lambda v: None if v <= 0 else v)(int(os.environ.get("ERN_LAUNCH_MAX_ROWS", str(1 << 21))))
 
@@ -48,17 +62,22 @@ def _rowmajor(t: torch.Tensor, what: str) -> torch.Tensor:
     return t
 
 
-def l2norm_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, want_bf16: bool = False
-                ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """``F.normalize(x, dim=-1).float()`` (run/test/test_fiq.py:45) and/or its bf16 rounding, on device."""
+def l2norm_rows(x: torch.Tensor, normalize: bool = True, want_f32: bool = True, want_bf16: bool = False,
+                want_f16: bool = False) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """``F.normalize(x, dim=-1).float()`` (run/test/test_fiq.py:45) and/or its 16-bit rounding (bf16, or fp16 with
+    ``want_f16``: saturating, for unit-norm features), on device.  Returns ``(fp32 | None, 16-bit | None)``."""
     x = _rowmajor(x, "x")
     if x.dtype != torch.float32:
         raise ErnError(f"l2norm_rows takes float32 features, got {x.dtype}")
     rows, dim = x.shape
     of = torch.empty((rows, dim), dtype=torch.float32, device=x.device) if want_f32 else None
-    ob = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    if want_bf16 and want_f16:
+        raise ErnError("l2norm_rows emits one 16-bit copy: want_bf16 or want_f16, not both")
+    ob = (torch.empty((rows, dim), dtype=torch.float16 if want_f16 else torch.bfloat16, device=x.device)
+          if (want_bf16 or want_f16) else None)
     with torch.cuda.device(x.device):
-        L.check(L.lib().ern_l2norm_rows(x.data_ptr(), rows, dim, x.stride(0), int(normalize), L.ptr(of), dim,
+        L.check(L.lib().ern_l2norm_rows(x.data_ptr(), rows, dim, x.stride(0),
+                                        int(bool(normalize)) | (NORM_OUT_F16 if want_f16 else 0), L.ptr(of), dim,
                                         L.ptr(ob), dim, L.stream_ptr(x.device)))
     launch_counter.add(1 if rows else 0)
     return of, ob
@@ -107,9 +126,7 @@ def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int 
     """
     q = _rowmajor(queries, "queries")
     g = _rowmajor(gallery, "gallery")
-    want = torch.float32 if mode == MODE_FP32 else torch.bfloat16
-    if q.dtype != want or g.dtype != want:
-        raise ErnError(f"mode {mode} takes {want} features, got queries {q.dtype} / gallery {g.dtype}")
+    dtype = _feature_dtype(q, g, mode)
     if q.shape[1] != g.shape[1]:
         raise ErnError(f"feature dims differ: {q.shape[1]} vs {g.shape[1]}")
     if q.device != g.device:
@@ -125,7 +142,6 @@ def sim_topk(queries: torch.Tensor, gallery: torch.Tensor, k: int, *, mode: int 
         L.require_cuda(exclude_ids, "exclude_ids")
         exclude_ids = exclude_ids.to(torch.int32).contiguous()
     lib = L.lib()
-    dtype = DTYPE_F32 if mode == MODE_FP32 else DTYPE_BF16
     with torch.cuda.device(dev):
         wsb = lib.ern_sim_topk_workspace_bytes(nq, dim, mode)
         ws = _workspace(wsb, dev)
@@ -151,9 +167,7 @@ def sim_topk_exchange(queries: torch.Tensor, gallery: torch.Tensor, k: int, peer
     buffer pointers, e.g. ``torch.distributed._symmetric_memory`` ``buffer_ptrs_dev``).  Returns ``status``."""
     q = _rowmajor(queries, "queries")
     g = _rowmajor(gallery, "gallery")
-    want = torch.float32 if mode == MODE_FP32 else torch.bfloat16
-    if q.dtype != want or g.dtype != want:
-        raise ErnError(f"mode {mode} takes {want} features")
+    dtype = _feature_dtype(q, g, mode)
     nq, dim = q.shape
     dev = q.device
     status = torch.empty(4, dtype=torch.int32, device=dev)
@@ -164,7 +178,7 @@ def sim_topk_exchange(queries: torch.Tensor, gallery: torch.Tensor, k: int, peer
         wsb = lib.ern_sim_topk_workspace_bytes(nq, dim, mode)
         ws = _workspace(wsb, dev)
         L.check(lib.ern_sim_topk_exchange(q.data_ptr(), nq, q.stride(0), g.data_ptr(), g.shape[0], g.stride(0), dim,
-                                          DTYPE_F32 if mode == MODE_FP32 else DTYPE_BF16, int(id_offset),
+                                          dtype, int(id_offset),
                                           L.ptr(exclude_ids), int(k), mode, rank_by, growth, peer_ptrs_dev, world,
                                           rank, status.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr(dev)))
         launch_counter.add(_sim_launches(nq, g.shape[0], k, growth, mode, dev))
@@ -223,9 +237,7 @@ def cirr_subset_recall(queries: torch.Tensor, gallery: torch.Tensor, members: to
     Returns ``(counts int32[len(ks)], rank int32[Q])``; rank -1 where the target is not a surviving member."""
     q = _rowmajor(queries, "queries")
     g = _rowmajor(gallery, "gallery")
-    if q.dtype != g.dtype or q.dtype not in (torch.float32, torch.bfloat16):
-        raise ErnError("queries/gallery must both be float32 or both bfloat16")
-    dtype = DTYPE_F32 if q.dtype == torch.float32 else DTYPE_BF16
+    dtype = _feature_dtype(q, g)
     members = members.to(torch.int32).contiguous()
     reference_ids = reference_ids.to(torch.int32).contiguous()
     target_ids = target_ids.to(torch.int32).contiguous()
@@ -249,14 +261,13 @@ def gather_scores(queries: torch.Tensor, gallery: torch.Tensor, ids: torch.Tenso
     shards gives the full [Q, m] matrix (CIRR group-member scores gathered from the owning shards)."""
     q = _rowmajor(queries, "queries")
     g = _rowmajor(gallery, "gallery")
-    if q.dtype != g.dtype or q.dtype not in (torch.float32, torch.bfloat16):
-        raise ErnError("queries/gallery must both be float32 or both bfloat16")
+    dtype = _feature_dtype(q, g)
     ids = ids.to(torch.int32).contiguous()
     nq, m = ids.shape
     out = torch.empty((nq, m), dtype=torch.float32, device=q.device)
     with torch.cuda.device(q.device):
         L.check(L.lib().ern_gather_scores(q.data_ptr(), nq, q.stride(0), g.data_ptr(), g.shape[0], g.stride(0), q.shape[1],
-                                          DTYPE_F32 if q.dtype == torch.float32 else DTYPE_BF16, int(id_offset),
+                                          dtype, int(id_offset),
                                           ids.data_ptr(), m, out.data_ptr(), L.stream_ptr(q.device)))
     launch_counter.add(1 if nq else 0)
     return out

@@ -48,6 +48,10 @@ extern "C" {
 /* element type of a feature matrix handed to the library */
 #define ERN_DTYPE_F32 0
 #define ERN_DTYPE_BF16 1
+#define ERN_DTYPE_F16 2  /* fp16 features on the tensor-core path (MODE_BF16): 11 mantissa bits instead of 8 at the same
+                            tcgen05 rate; for unit-norm features the range is no concern (north_star: "bf16/fp16") */
+/* ern_l2norm_rows: OR into `normalize` to make the 16-bit output fp16 instead of bf16 */
+#define ERN_NORM_OUT_F16 2
 
 /* what a candidate is ranked by */
 #define ERN_RANK_SIMILARITY 0 /* s = <q, g>                                                       */
@@ -70,7 +74,7 @@ ERN_API const char* ern_last_error(void);
 ERN_API int ern_device_check(int device);
 
 /* ---------------------------------------------------------------------------------------------
- * Row L2-normalise (+ optional bf16 cast).
+ * Row L2-normalise (+ optional 16-bit cast: bf16, or fp16 with normalize | ERN_NORM_OUT_F16).
  * Replaces F.normalize(index_features, dim=-1).float() (run/test/test_fiq.py:45 and twins),
  * eps = 1e-12 as torch's default.  Either output may be NULL.  ld* are row strides in elements.
  * ------------------------------------------------------------------------------------------- */

@@ -120,9 +120,10 @@ class SeededClip:
 TIE_TOL = 2.2e-6   # fp32 accumulation order + the rounding of 1 - s: ranks may differ only inside such gaps
 
 
-def rounded(t):
-    """What the bf16 tail actually scores: the fp32 features rounded to bf16 (metrics._operands), upcast again."""
-    return t.detach().float().cpu().bfloat16().float()
+def rounded(t, dtype=torch.bfloat16):
+    """What the 16-bit tail actually scores: the fp32 features rounded to bf16 (or fp16 with precision="fp16";
+    metrics._operands), upcast again."""
+    return t.detach().float().cpu().to(dtype).float()
 
 
 def unique_oracle_with_ties(pred_r, gal_r, names, tgt_names, ks, anyhit=False, tol=TIE_TOL):

@@ -37,6 +37,9 @@ def test_version_and_constants():
     assert int(re.search(r"#define ERN_SORT_CAP (\d+)", src).group(1)) == _lib.SORT_CAP
     assert int(re.search(r"#define ERN_DENSE_ROWS (\d+)", src).group(1)) == _lib.DENSE_ROWS
     assert int(re.search(r"#define ERN_QUERY_BATCH (\d+)", src).group(1)) == _lib.QUERY_BATCH
+    for name in ("DTYPE_F32", "DTYPE_BF16", "DTYPE_F16", "NORM_OUT_F16", "MODE_BF16", "MODE_FP32", "RANK_SIMILARITY",
+                 "RANK_REFERENCE"):
+        assert int(re.search(rf"#define ERN_{name} (\d+)", src).group(1)) == getattr(_lib, name), name
     # candidate storage of one query batch: a 256-slot prefix + one 256-slot segment per CTA pair (74 on a B200)
     one_batch = lib.ern_sim_topk_workspace_bytes(4096, 640, 0)
     assert one_batch >= 4096 * (_lib.DENSE_ROWS + 74 * _lib.SEG_CAP) * 8

@@ -74,6 +74,23 @@ def test_bf16_mode_is_exact_on_its_own_operands(cuda_device, name):
         assert abs(got - ref) <= 100.0 * nr / q + 1e-9, (k, got, ref, nr)
 
 
+@pytest.mark.parametrize("name", ["fiq640", "f200k640", "cirr640"])
+def test_fp16_tail_is_exact_on_its_own_operands(cuda_device, name):
+    """precision="fp16": the same tensor-core kernels on fp16-rounded operands (ERN_DTYPE_F16).  The tuple must equal
+    the oracle's on the same fp16-rounded operands except inside near-ties, as for bf16 above."""
+    from helpers import assert_tuple_within_ties, cirr_oracle_with_ties, rounded, unique_oracle_with_ties
+    z, meta, ds, feats, local, names, model = build(name, cuda_device, "bf16")
+    kind, q, dim = meta["kind"], meta["q"], meta["dim"]
+    out = FN[kind](ds, FakeClip(dim), feats, local, names, model, cuda_device, dim, 32, 0, "RN50x4", precision="fp16")
+    pred_r = rounded(torch.from_numpy(z["pred"]), torch.float16)
+    gal_r = rounded(metrics.prepare_gallery(feats, local, model, cuda_device), torch.float16)
+    if kind == "cirr":
+        want, near = cirr_oracle_with_ties(pred_r, gal_r, names, ds.ref, ds.tgt, ds.members)
+    else:
+        want, near = unique_oracle_with_ties(pred_r, gal_r, names, ds.tgt, KS[kind], anyhit=(kind == "200k"))
+    assert_tuple_within_ties(out, want, near, q)
+
+
 def test_8_argument_form_and_print(cuda_device, capsys):
     z, meta, ds, feats, local, names, model = build("fiq640", cuda_device, "fp32")
     metrics.set_precision("fp32")

@@ -20,11 +20,11 @@ def unit(seed, rows, dim):
     return syn.features(seed, rows, dim, unit=True)
 
 
-def run_case(dev, q, n, dim, k, mode, rank_by=RANK_REFERENCE, exclude=None, growth=8, seed=0):
+def run_case(dev, q, n, dim, k, mode, rank_by=RANK_REFERENCE, exclude=None, growth=8, seed=0, cast=torch.bfloat16):
     pred, gal = unit(seed + 1, q, dim), unit(seed + 2, n, dim)
-    if mode == MODE_BF16:
-        pred_o, gal_o = pred.bfloat16().float(), gal.bfloat16().float()
-        qd, gd = pred.bfloat16().to(dev), gal.bfloat16().to(dev)
+    if mode == MODE_BF16:       # the tensor-core mode: bf16 operands, or fp16 (cast=torch.float16)
+        pred_o, gal_o = pred.to(cast).float(), gal.to(cast).float()
+        qd, gd = pred.to(cast).to(dev), gal.to(cast).to(dev)
         tol = TOL_BF16_SAME_INPUTS
     else:
         pred_o, gal_o = pred, gal
@@ -66,6 +66,33 @@ def test_bf16_single_cta_matches_oracle(cuda_device, q, n, dim, k):
 def test_bf16_cta_pair_matches_oracle(cuda_device, q, n, dim, k):
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q > 128 -> cta_group::2 kernel
     assert stats["exact_frac"] > 0.99
+
+
+@pytest.mark.parametrize("q,n,dim,k", [(100, 5000, 640, 100), (5, 130, 64, 10), (300, 5000, 640, 100),
+                                       (2017, 3817, 640, 51), (700, 30000, 768, 100)])
+def test_fp16_operands_match_oracle(cuda_device, q, n, dim, k):
+    # ERN_DTYPE_F16: the same tcgen05 kernels (1-CTA and CTA pair) with the fp16 operand format; the oracle gets the
+    # same fp16-rounded operands, so only the accumulation order differs
+    stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16, cast=torch.float16)
+    assert stats["exact_frac"] > 0.99
+
+
+def test_fp16_operands_are_closer_to_fp32_than_bf16(cuda_device):
+    # unit-norm 640-d features: fp16 keeps 11 mantissa bits (bf16: 8), and nothing is near its range limits
+    q, n, dim, k = 256, 20000, 640, 100
+    pred, gal = unit(11, q, dim), unit(12, n, dim)
+    v32, i32, _, _ = ops.sim_topk(pred.to(cuda_device), gal.to(cuda_device), k, mode=MODE_FP32)
+    err = {}
+    for cast in (torch.float16, torch.bfloat16):
+        qd, gd = pred.to(cast).to(cuda_device), gal.to(cast).to(cuda_device)
+        assert ops.gather_scores(qd, gd, i32[:, :50]).sub(v32[:, :50]).abs().max().item() < (2e-4 if cast == torch.float16 else 2e-3)
+        v, _, _, _ = ops.sim_topk(qd, gd, k)
+        err[cast] = (v - v32).abs().max().item()        # k-th best values side by side
+    assert err[torch.float16] < 2e-4 and err[torch.float16] < err[torch.bfloat16]
+    with pytest.raises(ops.ErnError):
+        ops.sim_topk(pred.half().to(cuda_device), gal.bfloat16().to(cuda_device), k)       # mixed 16-bit types
+    with pytest.raises(ops.ErnError):
+        ops.sim_topk(pred.half().to(cuda_device), gal.half().to(cuda_device), k, mode=MODE_FP32)
 
 
 def test_bf16_similarity_ranking_and_exclusion(cuda_device):
