@@ -61,11 +61,6 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void lds128(uint32_t smem_addr, uint32_t (&r)[4]) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr) : "memory");
 }
-// Ask L2 to fetch `bytes` (multiple of 16, 16-byte aligned) starting at `gptr`: no register, no shared memory, no
-// completion to wait for -- the later cp.async of the same lines then hit in L2.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 // K blocks in flight per thread: what fits into ~190 KB of shared memory (a slot is 16 bytes per thread; a K block
 // needs kNTiles weight slots and, for bf16 activations, 2 * kMTiles activation slots)
 constexpr int stages_for(int m_tiles, int n_tiles) {
@@ -85,7 +80,7 @@ __device__ __forceinline__ void gemm_phase(AfterPrologue after_prologue, const T
                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int64_t ldo,
                                            const float* __restrict__ wg, float* __restrict__ partial, int n_ctas,
                                            float (*red)[32], float (*tile)[8 * kNTiles + 1], uint32_t wring,
-                                           uint32_t xtile, uint32_t xpitch, bool weights_first) {
+                                           uint32_t xtile, uint32_t xpitch) {
   constexpr int kCols = 8 * kNTiles;
   constexpr int kRows = 16 * kMTiles;
   constexpr int kAcc = kMTiles * kNTiles * 4;                 // fp32 accumulators per thread
@@ -135,52 +130,25 @@ __device__ __forceinline__ void gemm_phase(AfterPrologue after_prologue, const T
   // memory channels for the same offsets at the same time (a sum does not care where the walk starts)
   const int rot = n_blocks > 0 ? static_cast<int>(blockIdx.x) % n_blocks : 0;
   auto kblock = [&](int kb) { const int b = kb + rot; return b >= n_blocks ? b - n_blocks : b; };
-  auto issue_weights = [&](int kb) {
+  auto issue = [&](int kb) {
     if (kb < n_blocks) {
       const int stage = kb % kStages;
       const int off = kblock(kb) * 32;
 #pragma unroll
       for (int j = 0; j < kNTiles; ++j) cp_async16(slot_addr(stage, j), wrow[j] + off);
-    }
-  };
-  auto issue_acts = [&](int kb) {
-    if (kActFifo && kb < n_blocks) {
-      const int stage = kb % kStages;
-      const int off = kblock(kb) * 32;
+      if (kActFifo) {
 #pragma unroll
-      for (int i = 0; i < kMTiles; ++i) {
-        if (oklo[i]) cp_async16(slot_addr(stage, kNTiles + 2 * i), xlo[i] + off);
-        if (okhi[i]) cp_async16(slot_addr(stage, kNTiles + 2 * i + 1), xhi[i] + off);
+        for (int i = 0; i < kMTiles; ++i) {
+          if (oklo[i]) cp_async16(slot_addr(stage, kNTiles + 2 * i), xlo[i] + off);
+          if (okhi[i]) cp_async16(slot_addr(stage, kNTiles + 2 * i + 1), xhi[i] + off);
+        }
       }
     }
-  };
-  auto issue = [&](int kb) {
-    issue_weights(kb);
-    issue_acts(kb);
     cp_async_commit();                                        // (an empty group keeps the wait_group arithmetic uniform)
   };
-  if (kActFifo && weights_first) {
-    // The weights do not depend on the previous phase: their first kStages - 1 blocks are requested BEFORE
-    // `after_prologue` (the grid barrier that publishes `raw`), the activations of the same blocks after it.  The
-    // prologue then holds 2 (kStages - 1) commit groups instead of kStages - 1; block kb is still complete once all but
-    // the kStages - 1 youngest groups are (its activation group -- or, from block kStages - 1 on, its joint group -- is
-    // the (kStages - 1 + kb)-th oldest either way), so the wait in the loop is unchanged.
 #pragma unroll
-    for (int kb = 0; kb < kStages - 1; ++kb) {
-      issue_weights(kb);
-      cp_async_commit();
-    }
-    after_prologue();
-#pragma unroll
-    for (int kb = 0; kb < kStages - 1; ++kb) {
-      issue_acts(kb);
-      cp_async_commit();
-    }
-  } else {
-#pragma unroll
-    for (int kb = 0; kb < kStages - 1; ++kb) issue(kb);
-    after_prologue();                                         // (phase A: the input tile is built while the weights fly)
-  }
+  for (int kb = 0; kb < kStages - 1; ++kb) issue(kb);
+  after_prologue();                                           // (phase A: the input tile is built while the weights fly)
   for (int kb = 0; kb < n_blocks; ++kb) {
     issue(kb + kStages - 1);
     uint32_t ralo[kMTiles][4], rahi[kMTiles][4];
@@ -275,16 +243,7 @@ struct HeadArgs {
   int64_t ldb;
   float* gate;               // [rows] or null
   unsigned long long* stamps;   // profiling aid or null
-  int flags;                 // kFlag* below (ERN_HEAD_FLAGS; default kDefaultFlags)
 };
-// Scheduling choices of the fused kernel; none of them changes a single bit of the result (same products, same sums,
-// same order).  Measured in profiles/r02_head_flags.jsonl.
-constexpr int kFlagPrefetchMask = 3;     // L2 prefetch of this CTA's phase-B weights (its slice of W1, 51 MB over the grid)
-                                         // while phase A -- 6.5 MB of weights, latency-bound -- leaves HBM idle:
-                                         // 0 = off, 1 = first thing in the kernel, 2 = after phase A's own weight
-                                         // requests, 3 = after phase A's input tile is built
-constexpr int kFlagWeightsFirst = 4;     // phase B requests its first weight blocks before the grid barrier
-constexpr int kDefaultFlags = 2 | kFlagWeightsFirst;
 
 // (profiling aid, ERN_HEAD_STAMP_PTR: CTA 0 writes %globaltimer at the phase boundaries)
 #define STAMP(i)                                                                                   \
@@ -308,24 +267,12 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   const int n_ctas = gridDim.x;
 
   STAMP(0);
-  // this CTA's slice of W1 (kCols rows of 8D bf16, contiguous): one bulk L2 prefetch per row (the instruction takes
-  // warp-uniform operands: lane 0 of warp w asks for rows w, w + 8, ...)
-  auto prefetch_w1 = [&]() {
-    if ((threadIdx.x & 31) == 0) {
-      const uint32_t row_bytes = static_cast<uint32_t>(hid) * 2u;          // hid % 64 == 0 => a multiple of 16
-      const char* base = reinterpret_cast<const char*>(a.pv.w1 + static_cast<int64_t>(blockIdx.x) * kCols * hid);
-      for (int r = threadIdx.x >> 5; r < kCols; r += kWarps) l2_prefetch_bulk(base + static_cast<int64_t>(r) * row_bytes, row_bytes);
-    }
-  };
-  const int pf = a.flags & kFlagPrefetchMask;
-  if (pf == 1) prefetch_w1();
   // ---- phase A: this CTA's columns of raw = relu([text | image] . [Wt ; Wi]^T + [bt ; bi])  (text half first, :90)
   // its input (text for the first half of the column blocks, image for the second) becomes a bf16 tile in shared
   // memory in one round trip: 16 rows x kMTiles, zero beyond the batch, row pitch 2 D + 64 bytes (conflict-free LDS.128)
   const uint32_t xpitch = static_cast<uint32_t>(a.dim) * 2u + 64u;
   const uint32_t xtile = wring + static_cast<uint32_t>(stages_for(kMTiles, kNTiles) * kNTiles * kThreads * 16);
   auto build_input_tile = [&]() {
-    if (pf == 2) prefetch_w1();
     const float* __restrict__ x = (static_cast<int>(blockIdx.x) * kCols < proj) ? a.text : a.image;
     const int chunks_per_row = a.dim / 8;
     const int total = 16 * kMTiles * chunks_per_row;
@@ -349,30 +296,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
                        "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3]) : "memory");
       }
     }
-    if (pf == 3) prefetch_w1();
     __syncthreads();
   };
   gemm_phase<float, kMTiles, kNTiles, false>(build_input_tile, a.text, a.image, a.dim, a.rows, a.dim, a.pv.wt, proj, a.pv.bt, a.raw, hid,
-                                             nullptr, nullptr, n_ctas, red, tile, wring, xtile, xpitch, false);
+                                             nullptr, nullptr, n_ctas, red, tile, wring, xtile, xpitch);
   // ---- grid barrier: every column of raw is in L2 before anybody reads a row of it
-  auto barrier_raw = [&]() {
-    STAMP(1);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      atomicAdd(&a.sync[0], 1u);
-      while (ld_acquire(&a.sync[0]) < static_cast<unsigned>(n_ctas)) {}
-    }
-    __syncthreads();
-    STAMP(2);
-  };
-  // ---- phase B: hidden layer + gate dot product over this CTA's columns.  With kFlagWeightsFirst the barrier sits
-  //      inside the phase, between the first weight requests and the first reads of raw (every thread is past phase A's
-  //      last shared-memory read by then: its epilogue starts with a block barrier).
-  const bool weights_first = (a.flags & kFlagWeightsFirst) != 0;
-  if (!weights_first) barrier_raw();
-  gemm_phase<__nv_bfloat16, kMTiles, kNTiles, true>([&] { if (weights_first) barrier_raw(); }, a.raw, a.raw, hid, a.rows, hid, a.pv.w1, hid, a.pv.b1, nullptr, 0,
-                                                    a.pv.w2, a.partial, n_ctas, red, tile, wring, 0u, 0u, weights_first);
+  STAMP(1);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&a.sync[0], 1u);
+    while (ld_acquire(&a.sync[0]) < static_cast<unsigned>(n_ctas)) {}
+  }
+  __syncthreads();
+  STAMP(2);
+  // ---- phase B: hidden layer + gate dot product over this CTA's columns
+  gemm_phase<__nv_bfloat16, kMTiles, kNTiles, true>([] {}, a.raw, a.raw, hid, a.rows, hid, a.pv.w1, hid, a.pv.b1, nullptr, 0,
+                                                    a.pv.w2, a.partial, n_ctas, red, tile, wring, 0u, 0u);
   // ---- second grid barrier, then phase C: CTA r turns row r's partials into the fused feature row
   STAMP(3);
   __threadfence();
@@ -508,8 +448,6 @@ int forward(const PackedView& pv, unsigned* sync, int dim, const float* image, c
     return e ? reinterpret_cast<unsigned long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }();
   a.stamps = stamps;
-  const char* fl = getenv("ERN_HEAD_FLAGS");                  // (read per call: tools/bench_head_small.py sweeps it)
-  a.flags = fl ? atoi(fl) : kDefaultFlags;
 #define ERN_FUSED(M)                                                         \
   (nt == 4 ? launch_fused<M, 4>(a, grid, st) : nt == 5 ? launch_fused<M, 5>(a, grid, st) : launch_fused<M, 6>(a, grid, st))
   if (rows <= 16) return ERN_FUSED(1);

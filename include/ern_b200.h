@@ -187,7 +187,8 @@ ERN_API int ern_dvr_encode(const ern_dvr_weights* w, int dim, int heads, int pat
  *           sorted_indices = torch.argsort(distances, dim=-1)` (run/test/test_fiq.py:49-50 and twins)
  * for the first k columns; the [Q,N] matrix is never materialised.
  *
- *   queries   [nq, dim]   row stride ldq,  dtype q_dtype (F32 for MODE_FP32; BF16 for MODE_BF16)
+ *   queries   [nq, dim]   row stride ldq,  dtype (ERN_DTYPE_F32 for MODE_FP32; ERN_DTYPE_BF16 or ERN_DTYPE_F16 for
+ *             MODE_BF16, the tensor-core mode: same kernels and speed, only the operand format differs)
  *   gallery   [n_rows, dim] row stride ldg, same dtype; n_rows rows of this shard
  *   id_offset global id of gallery row 0 (shard offset); ids returned are global
  *   exclude_id_dev (nullable) [nq] global id removed from query q's ranking (CIRR reference image,

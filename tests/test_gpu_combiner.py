@@ -73,28 +73,6 @@ def test_small_batches_weight_streaming_path(cuda_device, dim, rows):
     assert torch.isfinite(out).all()
 
 
-@pytest.mark.parametrize("dim,rows", [(640, 32), (640, 7), (512, 64), (768, 33)])
-def test_small_batch_scheduling_flags_do_not_change_a_bit(cuda_device, monkeypatch, dim, rows):
-    """ERN_HEAD_FLAGS only moves requests in time (L2 prefetch of the hidden-layer weights during phase A, phase B's
-    first weight blocks requested before the grid barrier): every setting must give the bit pattern of flags 0."""
-    m = make(dim, 17, "bf16", cuda_device)
-    img, txt = syn.features(18, rows, dim).to(cuda_device), syn.features(19, rows, dim, unit=True).to(cuda_device)
-    outs = {}
-    with torch.no_grad():
-        for flags in (0, 1, 2, 3, 4, 5, 6, 7, None):
-            if flags is None:
-                monkeypatch.delenv("ERN_HEAD_FLAGS", raising=False)     # the library reads it on every call
-            else:
-                monkeypatch.setenv("ERN_HEAD_FLAGS", str(flags))
-            for _ in range(3):                                           # (also re-uses the rotating barrier counters)
-                o, ob = m(img, txt, want_bf16=True)
-                outs.setdefault(flags, []).append((o.clone(), ob.clone()))
-    torch.cuda.synchronize()
-    for flags, lst in outs.items():
-        for o, ob in lst:
-            assert torch.equal(o, outs[0][0][0]) and torch.equal(ob, outs[0][0][1]), flags
-
-
 def test_small_batch_head_on_concurrent_streams(cuda_device):
     """The fused small-batch kernel synchronises its CTAs through counters that live behind the packed weights (15
     rotating, self-resetting sets): forwards of ONE module issued on several streams at once must neither hang nor mix
