@@ -14,6 +14,11 @@ pytestmark = pytest.mark.gpu
 # where the ORACLE's own scores are closer than this.
 TOL_FP32 = 2e-6
 TOL_BF16_SAME_INPUTS = 2e-6   # oracle fed the same bf16-rounded operands: only accumulation order differs
+# Secondary check next to compare_topk's rank-wise gap rule: the fraction of positions that are IDENTICAL to the
+# oracle's.  Observed minimum over every parametrised case below (tools/exact_frac_census.py,
+# profiles/r02_exact_frac_census.jsonl): 1.0 in fp32, 0.9996 with bf16 and 0.9998 with fp16 operands -- the rest are
+# swaps inside < 2e-6 near-ties.
+EXACT_FRAC_16BIT = 0.999
 
 
 def unit(seed, rows, dim):
@@ -58,14 +63,14 @@ def test_fp32_validation_mode_matches_oracle(cuda_device, q, n, dim, k):
                                        (5, 130, 64, 10), (1, 4000, 640, 1), (100, 9000, 768, 50), (64, 3000, 704, 20)])
 def test_bf16_single_cta_matches_oracle(cuda_device, q, n, dim, k):
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q <= 128 -> 1-CTA tcgen05 kernel
-    assert stats["exact_frac"] > 0.99
+    assert stats["exact_frac"] > EXACT_FRAC_16BIT
 
 
 @pytest.mark.parametrize("q,n,dim,k", [(300, 5000, 640, 100), (129, 257, 640, 50), (2017, 3817, 640, 51),
                                        (512, 40000, 512, 100), (1000, 20000, 128, 128), (700, 30000, 768, 100)])
 def test_bf16_cta_pair_matches_oracle(cuda_device, q, n, dim, k):
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16)   # q > 128 -> cta_group::2 kernel
-    assert stats["exact_frac"] > 0.99
+    assert stats["exact_frac"] > EXACT_FRAC_16BIT
 
 
 @pytest.mark.parametrize("q,n,dim,k", [(100, 5000, 640, 100), (5, 130, 64, 10), (300, 5000, 640, 100),
@@ -74,7 +79,7 @@ def test_fp16_operands_match_oracle(cuda_device, q, n, dim, k):
     # ERN_DTYPE_F16: the same tcgen05 kernels (1-CTA and CTA pair) with the fp16 operand format; the oracle gets the
     # same fp16-rounded operands, so only the accumulation order differs
     stats, *_ = run_case(cuda_device, q, n, dim, k, MODE_BF16, cast=torch.float16)
-    assert stats["exact_frac"] > 0.99
+    assert stats["exact_frac"] > EXACT_FRAC_16BIT
 
 
 def test_fp16_operands_are_closer_to_fp32_than_bf16(cuda_device):
@@ -162,6 +167,29 @@ def test_shard_merge_equals_global(cuda_device):
     parts = [ops.sim_topk(pred, gal[a:b], k, id_offset=a, want_keys=True)[2] for a, b in zip(bounds[:-1], bounds[1:])]
     vals, ids, keys = ops.topk_merge(torch.stack(parts), k)
     assert torch.equal(ids, ids_all) and torch.equal(keys, keys_all)
+
+
+@pytest.mark.parametrize("q,world", [(140, 3), (100, 2), (600, 4), (4200, 2)])   # 4200: two query batches
+def test_fused_exchange_stores_on_one_gpu(cuda_device, q, world):
+    # ern_sim_topk_exchange on ONE device: the `world` gathered buffers all live here and the peer-pointer table is
+    # built by hand (what torch symmetric memory hands out on a multi-GPU box, tools/test_exchange.py).  Every "rank"
+    # scores its shard and its last selection launch stores the keys into slot `rank` of EVERY buffer: each buffer
+    # must end up as the stack of the per-shard key lists, bit for bit, and merge to the global top-k.
+    n, k, dim = 9001, 100, 640
+    pred, gal = unit(23, q, dim).bfloat16().to(cuda_device), unit(24, n, dim).bfloat16().to(cuda_device)
+    _, ids_all, keys_all, _ = ops.sim_topk(pred, gal, k, want_keys=True)
+    per = (n + world - 1) // world
+    bounds = [(min(r * per, n), min((r + 1) * per, n)) for r in range(world)]
+    parts = torch.stack([ops.sim_topk(pred, gal[a:b], k, id_offset=a, want_keys=True)[2] for a, b in bounds])
+    bufs = [torch.full((world, q, k), -7, dtype=torch.int64, device=cuda_device) for _ in range(world)]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=cuda_device)
+    for r, (a, b) in enumerate(bounds):
+        st = ops.sim_topk_exchange(pred, gal[a:b], k, table.data_ptr(), world, r, id_offset=a)
+        assert st.cpu().tolist() == [0, 0, 0, 0]
+    for buf in bufs:
+        assert torch.equal(buf, parts)
+        _, ids, keys = ops.topk_merge(buf, k)
+        assert torch.equal(ids, ids_all) and torch.equal(keys, keys_all)
 
 
 def test_recall_kernels_match_oracle(cuda_device):
