@@ -61,13 +61,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void lds128(uint32_t smem_addr, uint32_t (&r)[4]) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr) : "memory");
 }
-// K blocks in flight per thread: what fits into ~190 KB of shared memory (a slot is 16 bytes per thread; a K block
-// needs kNTiles weight slots and, for bf16 activations, 2 * kMTiles activation slots)
+// K blocks in flight per thread: what fits into kRingBudget bytes of shared memory (a slot is 16 bytes per thread; a K
+// block needs kNTiles weight slots and, for bf16 activations, 2 * kMTiles activation slots)
+// (more is not better: with a 220 KB budget -- 6 instead of 5 stages at 32 rows, 4 instead of 3 at 64 -- every size got
+// slower, 26.3 -> 27.6 us at 32 rows; profiles/r02_head_micro_ab.jsonl)
+constexpr int kRingBudget = 190 * 1024;
 constexpr int stages_for(int m_tiles, int n_tiles) {
   const int per_stage = (n_tiles + 2 * m_tiles) * 256 * 16;
-  const int s = (190 * 1024) / per_stage;
+  const int s = kRingBudget / per_stage;
   return s > 8 ? 8 : s;
 }
+// static shared memory of fused_head_kernel: tile[16 M][8 N + 1] + sred[40]
+constexpr int static_smem_for(int m_tiles, int n_tiles) { return (16 * m_tiles * (8 * n_tiles + 1) + 40) * 4; }
 
 // C[rows, n0 .. n0 + 8*kNTiles) = relu(X . W^T + bias) for this CTA's column block.
 //   X  : [rows, K] (TIn = float: converted to bf16 on the fly; or bf16), columns < n_split read x0, the others x1
@@ -79,7 +84,7 @@ __device__ __forceinline__ void gemm_phase(AfterPrologue after_prologue, const T
                                            int K, const __nv_bfloat16* __restrict__ W, int n_split,
                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int64_t ldo,
                                            const float* __restrict__ wg, float* __restrict__ partial, int n_ctas,
-                                           float (*red)[32], float (*tile)[8 * kNTiles + 1], uint32_t wring,
+                                           float (*tile)[8 * kNTiles + 1], uint32_t wring, float* ring_f32,
                                            uint32_t xtile, uint32_t xpitch) {
   constexpr int kCols = 8 * kNTiles;
   constexpr int kRows = 16 * kMTiles;
@@ -146,6 +151,16 @@ __device__ __forceinline__ void gemm_phase(AfterPrologue after_prologue, const T
     }
     cp_async_commit();                                        // (an empty group keeps the wait_group arithmetic uniform)
   };
+  // The epilogue needs this CTA's kCols entries of the bias (and gate) vector only after the K loop; from a cold L2 that
+  // would be an HBM round trip at the end of the phase (ncu: 8 % of the kernel's stall samples sat on the two FADDs that
+  // consume them).  Thread c < kCols fetches entry c now and parks it in a register across the loop.
+  // (only for <= 32 rows: at 33..64 rows, with 80 accumulators per thread, it measured 1.3 us slower)
+  constexpr bool kPreload = kMTiles <= 2;
+  float pre_bias = 0.f, pre_gate = 0.f;
+  if (kPreload && threadIdx.x < kCols) {
+    pre_bias = __ldg(bias + n0 + threadIdx.x);
+    if (kGate) pre_gate = __ldg(wg + n0 + threadIdx.x);
+  }
 #pragma unroll
   for (int kb = 0; kb < kStages - 1; ++kb) issue(kb);
   after_prologue();                                           // (phase A: the input tile is built while the weights fly)
@@ -188,29 +203,36 @@ __device__ __forceinline__ void gemm_phase(AfterPrologue after_prologue, const T
   cp_async_wait<0>();
 
   // ---- sum the warps' partial tiles in a fixed order (deterministic), then the epilogue -----------------------------
-  __syncthreads();                                            // (red / tile may still be read by the previous phase)
-  for (int w = 0; w < ks; ++w) {
-    if (warp == w) {
+  // Every thread's copies have landed and, after this barrier, nobody reads the ring (or phase A's input tile) any more:
+  // the ring now holds the ks partial tiles, one per warp, in fragment order [warp][element][lane], and behind them the
+  // bias / gate entries fetched before the loop.  After ONE more barrier all 256 threads add the partials up in warp
+  // order -- the same order, hence the same bits, as accumulating warp after warp with a barrier in between, which is what
+  // this replaced (ks + 1 barriers with one warp working at a time: 1.8 us of the 28.5 at 32 rows).
+  __syncthreads();
+  float* svec = ring_f32 + kWarps * (kAcc * 32);
+  if (warp < ks) {
+    float* mine = ring_f32 + warp * (kAcc * 32) + lane;
 #pragma unroll
-      for (int i = 0; i < kMTiles; ++i)
+    for (int i = 0; i < kMTiles; ++i)
 #pragma unroll
-        for (int j = 0; j < kNTiles; ++j)
+      for (int j = 0; j < kNTiles; ++j)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float* dst = &red[(i * kNTiles + j) * 4 + c][lane];
-            *dst = (w == 0) ? acc[i][j][c] : *dst + acc[i][j][c];
-          }
-    }
-    __syncthreads();
+        for (int c = 0; c < 4; ++c) mine[((i * kNTiles + j) * 4 + c) * 32] = acc[i][j][c];
   }
+  if (kPreload && threadIdx.x < kCols) {
+    svec[threadIdx.x] = pre_bias;
+    if (kGate) svec[kCols + threadIdx.x] = pre_gate;
+  }
+  __syncthreads();
   for (int idx = threadIdx.x; idx < kAcc * 32; idx += kThreads) {
     const int e = idx >> 5, l = idx & 31;
-    float v = red[e][l];
+    float v = ring_f32[idx];
+    for (int w = 1; w < ks; ++w) v += ring_f32[w * (kAcc * 32) + idx];
     const int c = e & 3, j = (e >> 2) % kNTiles, i = (e >> 2) / kNTiles;
     const int row = 16 * i + (l >> 2) + 8 * (c >> 1);
     const int col = 8 * j + 2 * (l & 3) + (c & 1);
-    v = fmaxf(v + bias[n0 + col], 0.f);
-    if (kGate) tile[row][col] = v * wg[n0 + col];
+    v = fmaxf(v + (kPreload ? svec[col] : bias[n0 + col]), 0.f);
+    if (kGate) tile[row][col] = v * (kPreload ? svec[kCols + col] : wg[n0 + col]);
     else if (row < rows) out[static_cast<int64_t>(row) * ldo + n0 + col] = __float2bfloat16_rn(v);
   }
   if (kGate) {
@@ -259,7 +281,7 @@ struct HeadArgs {
 template <int kMTiles, int kNTiles>
 __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs a) {
   constexpr int kCols = 8 * kNTiles;
-  __shared__ float red[kMTiles * kNTiles * 4][32];           // the CTA's output tile in fragment order
+  __shared__ float sred[32 + kWarps];                        // phase C: gate, per-warp sums of squares
   __shared__ float tile[16 * kMTiles][kCols + 1];
   extern __shared__ __align__(16) uint8_t wring_raw[];        // stages_for(M, N) stages of (kNTiles + 2 kMTiles) slots x 256 threads x 16 B
   const uint32_t wring = static_cast<uint32_t>(__cvta_generic_to_shared(wring_raw));
@@ -299,12 +321,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
     __syncthreads();
   };
   gemm_phase<float, kMTiles, kNTiles, false>(build_input_tile, a.text, a.image, a.dim, a.rows, a.dim, a.pv.wt, proj, a.pv.bt, a.raw, hid,
-                                             nullptr, nullptr, n_ctas, red, tile, wring, xtile, xpitch);
+                                             nullptr, nullptr, n_ctas, tile, wring, reinterpret_cast<float*>(wring_raw), xtile, xpitch);
   // ---- grid barrier: every column of raw is in L2 before anybody reads a row of it
+  // <= 32 rows: the block barrier orders every thread's stores before thread 0's fence, which publishes them gpu-wide
+  // together with the arrival (the cooperative-groups grid.sync pattern); 33..64 rows keep a fence in every thread.
+  // Measured together with the early bias fetch: -0.9 us at 1..16 rows, even at 32, +1.3 us at 64 rows
+  // (profiles/r02_head_micro_ab.jsonl).
+  constexpr bool kOneFence = kMTiles <= 2;
   STAMP(1);
-  __threadfence();
+  if (!kOneFence) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (kOneFence) __threadfence();
     atomicAdd(&a.sync[0], 1u);
     while (ld_acquire(&a.sync[0]) < static_cast<unsigned>(n_ctas)) {}
   }
@@ -312,13 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   STAMP(2);
   // ---- phase B: hidden layer + gate dot product over this CTA's columns
   gemm_phase<__nv_bfloat16, kMTiles, kNTiles, true>([] {}, a.raw, a.raw, hid, a.rows, hid, a.pv.w1, hid, a.pv.b1, nullptr, 0,
-                                                    a.pv.w2, a.partial, n_ctas, red, tile, wring, 0u, 0u);
+                                                    a.pv.w2, a.partial, n_ctas, tile, wring, reinterpret_cast<float*>(wring_raw), 0u, 0u);
   // ---- second grid barrier, then phase C: CTA r turns row r's partials into the fused feature row
   STAMP(3);
-  __threadfence();
+  if (!kOneFence) __threadfence();
   __syncthreads();
   const bool finisher = static_cast<int>(blockIdx.x) < a.rows;
   if (threadIdx.x == 0) {
+    if (kOneFence) __threadfence();
     atomicAdd(&a.sync[1], 1u);
     if (finisher)
       while (ld_acquire(&a.sync[1]) < static_cast<unsigned>(n_ctas)) {}
@@ -328,7 +357,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   if (finisher) {
     const int r = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sred = &red[0][0];                                 // (phase B is done with it)
     // the row's inputs do not depend on the gate: fetch them while the partials are summed
     const float* im = a.image + static_cast<int64_t>(r) * a.dim;
     const float* tx = a.text + static_cast<int64_t>(r) * a.dim;
@@ -415,6 +443,8 @@ static int launch_fused(const HeadArgs& a, int grid, cudaStream_t st) {
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
   constexpr int kRing = stages_for(kMTiles, kNTiles) * (kNTiles + 2 * kMTiles) * kThreads * 16;
+  static_assert(kRing + static_smem_for(kMTiles, kNTiles) <= 232448, "ring + static shared memory exceed what a CTA may own");
+  static_assert((kWarps * kMTiles * kNTiles * 4 * 32 + 16 * kNTiles) * 4 <= kRing, "the epilogue's partial tiles must fit into the ring");
   static std::atomic<bool> configured[64];                     // opt-in shared-memory size is a per-device attribute
   int dev = 0;
   ERN_CUDA(cudaGetDevice(&dev));
