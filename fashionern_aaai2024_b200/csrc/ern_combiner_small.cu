@@ -71,8 +71,12 @@ constexpr int stages_for(int m_tiles, int n_tiles) {
   const int s = kRingBudget / per_stage;
   return s > 8 ? 8 : s;
 }
+// Early bias fetch + one fence per CTA, for every batch size.  (An A/B build that kept the old form above 32 rows was
+// 2.2 us slower at 64 rows once the ring was 128-byte aligned: profiles/r02_head_align_ab.jsonl.  An earlier
+// measurement that said the opposite had the ring misaligned, see fused_head_kernel.)
+constexpr bool lean_form(int) { return true; }
 // static shared memory of fused_head_kernel: tile[16 M][8 N + 1] + sred[40]
-constexpr int static_smem_for(int m_tiles, int n_tiles) { return (16 * m_tiles * (8 * n_tiles + 1) + 40) * 4; }
+constexpr int static_smem_for(int m_tiles, int n_tiles) { return ((16 * m_tiles * (8 * n_tiles + 1) + 40) * 4 + 127) / 128 * 128; }
 
 // C[rows, n0 .. n0 + 8*kNTiles) = relu(X . W^T + bias) for this CTA's column block.
 //   X  : [rows, K] (TIn = float: converted to bf16 on the fly; or bf16), columns < n_split read x0, the others x1
@@ -154,8 +158,7 @@ __device__ __forceinline__ void gemm_phase(AfterPrologue after_prologue, const T
   // The epilogue needs this CTA's kCols entries of the bias (and gate) vector only after the K loop; from a cold L2 that
   // would be an HBM round trip at the end of the phase (ncu: 8 % of the kernel's stall samples sat on the two FADDs that
   // consume them).  Thread c < kCols fetches entry c now and parks it in a register across the loop.
-  // (only for <= 32 rows: at 33..64 rows, with 80 accumulators per thread, it measured 1.3 us slower)
-  constexpr bool kPreload = kMTiles <= 2;
+  constexpr bool kPreload = lean_form(kMTiles);
   float pre_bias = 0.f, pre_gate = 0.f;
   if (kPreload && threadIdx.x < kCols) {
     pre_bias = __ldg(bias + n0 + threadIdx.x);
@@ -283,7 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   constexpr int kCols = 8 * kNTiles;
   __shared__ float sred[32 + kWarps];                        // phase C: gate, per-warp sums of squares
   __shared__ float tile[16 * kMTiles][kCols + 1];
-  extern __shared__ __align__(16) uint8_t wring_raw[];        // stages_for(M, N) stages of (kNTiles + 2 kMTiles) slots x 256 threads x 16 B
+  // 128-byte aligned: a warp's 512 contiguous bytes of a slot must be four shared-memory lines, not five.  The static
+  // arrays in front of it end at a multiple of 32 only; when `red` (10-20 KB, a multiple of 128 by luck) left the kernel
+  // the ring slid to offset 32 mod 128 and the 64-row case went 36.3 -> 40.5 us until this attribute pinned it
+  // (34.9 us with it).
+  extern __shared__ __align__(128) uint8_t wring_raw[];        // stages_for(M, N) stages of (kNTiles + 2 kMTiles) slots x 256 threads x 16 B
   const uint32_t wring = static_cast<uint32_t>(__cvta_generic_to_shared(wring_raw));
   const int hid = 8 * a.dim, proj = 4 * a.dim;
   const int n_ctas = gridDim.x;
@@ -323,11 +330,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_head_kernel(const HeadArgs 
   gemm_phase<float, kMTiles, kNTiles, false>(build_input_tile, a.text, a.image, a.dim, a.rows, a.dim, a.pv.wt, proj, a.pv.bt, a.raw, hid,
                                              nullptr, nullptr, n_ctas, tile, wring, reinterpret_cast<float*>(wring_raw), xtile, xpitch);
   // ---- grid barrier: every column of raw is in L2 before anybody reads a row of it
-  // <= 32 rows: the block barrier orders every thread's stores before thread 0's fence, which publishes them gpu-wide
-  // together with the arrival (the cooperative-groups grid.sync pattern); 33..64 rows keep a fence in every thread.
-  // Measured together with the early bias fetch: -0.9 us at 1..16 rows, even at 32, +1.3 us at 64 rows
-  // (profiles/r02_head_micro_ab.jsonl).
-  constexpr bool kOneFence = kMTiles <= 2;
+  // The block barrier orders every thread's stores before thread 0's fence, which publishes them gpu-wide together with
+  // the arrival (the cooperative-groups grid.sync pattern) instead of a fence in each of the 256 threads.  Measured
+  // together with the early bias fetch: -0.9 us at 1..16 rows, -2.2 us at 64 rows (profiles/r02_head_micro_ab.jsonl,
+  // r02_head_align_ab.jsonl).
+  constexpr bool kOneFence = lean_form(kMTiles);
   STAMP(1);
   if (!kOneFence) __threadfence();
   __syncthreads();
