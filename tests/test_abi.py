@@ -67,6 +67,28 @@ def test_cpu_tensors_are_refused():
         m(x, x)
 
 
+def test_feature_dtype_rules_of_the_scoring_call():
+    # host-side argument checks of ops.sim_topk and friends (they run before any device work): both matrices share one
+    # type; fp32 validation mode takes float32, the tensor-core mode bfloat16 or float16 (ERN_DTYPE_F16)
+    from fashionern_aaai2024_b200 import metrics
+    f32, bf, h = torch.zeros(2, 64), torch.zeros(2, 64, dtype=torch.bfloat16), torch.zeros(2, 64, dtype=torch.float16)
+    assert ops._feature_dtype(f32, f32, _lib.MODE_FP32) == _lib.DTYPE_F32
+    assert ops._feature_dtype(bf, bf, _lib.MODE_BF16) == _lib.DTYPE_BF16
+    assert ops._feature_dtype(h, h, _lib.MODE_BF16) == _lib.DTYPE_F16
+    assert ops._feature_dtype(h, h) == _lib.DTYPE_F16                   # (calls without a mode: subset recall, gathers)
+    for q, g, mode in ((h, bf, _lib.MODE_BF16), (f32, f32, _lib.MODE_BF16), (h, h, _lib.MODE_FP32), (bf, bf, _lib.MODE_FP32),
+                       (f32.double(), f32.double(), _lib.MODE_FP32), (f32, bf, None)):
+        with pytest.raises(_lib.ErnError):
+            ops._feature_dtype(q, g, mode)
+    for p in ("bf16", "fp16", "fp32"):
+        metrics.set_precision(p)
+    metrics.set_precision("bf16")
+    with pytest.raises(_lib.ErnError):
+        metrics.set_precision("fp8")
+    with pytest.raises(_lib.ErnError):
+        metrics._operands(f32, f32, "int8")
+
+
 def test_training_mode_is_refused():
     m = CombinerSimple(64, 256, 512)
     m.train()
