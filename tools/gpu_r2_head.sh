@@ -1,5 +1,8 @@
 #!/bin/bash
 # fused small-batch head: parity tests of the in-tree build, then A/B timing against the variant builds in ab_libs/
+# (ab_libs/ is git-ignored: a variant is the in-tree objects with ern_combiner_small.cu recompiled under a -D switch,
+#  as tools/build_trace_lib.sh does for the scoring kernel; the switches of the measured variants lived only in the
+#  commits named in DESIGN.md 4.3a / profiles/r02_notes.md)
 mkdir -p gpurun_out
 timeout 200 python -m pytest tests/test_gpu_combiner.py -q -m gpu 2>&1 | tail -1
 for lib in "" ab_libs/libern_lean2.so; do
